@@ -1,0 +1,121 @@
+"""Exact-rational referee for the boolean / index outputs — TEST INFRASTRUCTURE ONLY.
+
+Independent of oracle/geo_oracle.c: it evaluates the *mathematical* definitions with
+fractions.Fraction (every f64 is an exact rational), using formulations different from the
+winding/orient2d ones the oracle restates, so agreement is evidence and not tautology.
+Pure-Python loops: small cases only.
+"""
+from __future__ import annotations
+
+from fractions import Fraction as F
+from typing import List, Sequence, Tuple
+
+Coord = Tuple[float, float]
+
+
+def orient_sign(a: Coord, b: Coord, c: Coord) -> int:
+    """sign of det [[ax-cx, ay-cy],[bx-cx, by-cy]] computed exactly."""
+    d = (F(a[0]) - F(c[0])) * (F(b[1]) - F(c[1])) - (F(a[1]) - F(c[1])) * (F(b[0]) - F(c[0]))
+    return (d > 0) - (d < 0)
+
+
+def _on_segment(p: Coord, s: Coord, e: Coord) -> bool:
+    px, py, sx, sy, ex, ey = map(F, (*p, *s, *e))
+    if (sx, sy) == (ex, ey):
+        return (px, py) == (sx, sy)
+    cross = (ex - sx) * (py - sy) - (ey - sy) * (px - sx)
+    if cross != 0:
+        return False
+    dot = (px - sx) * (ex - sx) + (py - sy) * (ey - sy)
+    return 0 <= dot <= (ex - sx) ** 2 + (ey - sy) ** 2
+
+
+def ring_position(p: Coord, ring: Sequence[Coord]) -> int:
+    """0 outside / 1 boundary / 2 inside (non-zero winding) for a closed ring, by exact ray casting."""
+    n = len(ring)
+    if n == 0:
+        return 0
+    if n == 1:
+        return 1 if tuple(ring[0]) == tuple(p) else 0
+    pts = list(ring)
+    if tuple(pts[0]) != tuple(pts[-1]):
+        pts.append(pts[0])
+    for s, e in zip(pts[:-1], pts[1:]):
+        if _on_segment(p, s, e):
+            return 1
+    px, py = F(p[0]), F(p[1])
+    wn = 0
+    for s, e in zip(pts[:-1], pts[1:]):
+        sx, sy, ex, ey = map(F, (*s, *e))
+        if sy <= py < ey:  # upward
+            xint = sx + (py - sy) * (ex - sx) / (ey - sy)
+            if xint > px:
+                wn += 1
+        elif ey <= py < sy:  # downward
+            xint = sx + (py - sy) * (ex - sx) / (ey - sy)
+            if xint > px:
+                wn -= 1
+    return 2 if wn != 0 else 0
+
+
+def polygon_contains(p: Coord, rings: Sequence[Sequence[Coord]]) -> bool:
+    """interior-only containment: inside exterior, strictly outside every hole."""
+    if not rings or len(rings[0]) == 0:
+        return False
+    if ring_position(p, rings[0]) != 2:
+        return False
+    return all(ring_position(p, h) == 0 for h in rings[1:])
+
+
+def segments_intersect(s0: Coord, e0: Coord, s1: Coord, e1: Coord) -> bool:
+    ax, ay, bx, by, cx, cy, dx, dy = map(F, (*s0, *e0, *s1, *e1))
+    rx, ry = bx - ax, by - ay
+    qx, qy = dx - cx, dy - cy
+    den = rx * qy - ry * qx
+    wx, wy = cx - ax, cy - ay
+    if den != 0:
+        t = (wx * qy - wy * qx) / den
+        u = (wx * ry - wy * rx) / den
+        return 0 <= t <= 1 and 0 <= u <= 1
+    # parallel or degenerate
+    if (rx, ry) == (0, 0):
+        return _on_segment(s0, s1, e1)
+    if (qx, qy) == (0, 0):
+        return _on_segment(s1, s0, e0)
+    if wx * ry - wy * rx != 0:
+        return False
+    rr = rx * rx + ry * ry
+    t0 = (wx * rx + wy * ry) / rr
+    t1 = t0 + (qx * rx + qy * ry) / rr
+    lo, hi = min(t0, t1), max(t0, t1)
+    return hi >= 0 and lo <= 1
+
+
+def linestrings_intersect(a: Sequence[Coord], b: Sequence[Coord]) -> bool:
+    for i in range(len(a) - 1):
+        for j in range(len(b) - 1):
+            if segments_intersect(a[i], a[i + 1], b[j], b[j + 1]):
+                return True
+    return False
+
+
+def convex_hull_vertices(pts: Sequence[Coord]) -> List[Coord]:
+    """strictly convex hull, CCW, starting at the lexicographic minimum (Andrew's chain, exact)."""
+    P = sorted(set((float(x), float(y)) for x, y in pts))
+    if len(P) <= 2:
+        return P
+
+    def cross(o, a, b):
+        return (F(a[0]) - F(o[0])) * (F(b[1]) - F(o[1])) - (F(a[1]) - F(o[1])) * (F(b[0]) - F(o[0]))
+
+    lower: List[Coord] = []
+    for p in P:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0:
+            lower.pop()
+        lower.append(p)
+    upper: List[Coord] = []
+    for p in reversed(P):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0:
+            upper.pop()
+        upper.append(p)
+    return lower[:-1] + upper[:-1]

@@ -1,0 +1,1083 @@
+/*
+ * geo_oracle.c — CPU oracle for the GeoSeries hot path.  TEST INFRASTRUCTURE ONLY (see geo_oracle.h).
+ *
+ * PARITY: pinned for contains() by spatial_index.rs:432-484 only; everything else PARITY UNPINNED.
+ * Each function cites (a) the reference call site whose behaviour it stands in for and (b) the
+ * third-party algorithm it restates ("recalled": restated from the published crate, source absent).
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fopenmp -fPIC -shared  (see oracle/Makefile).
+ * -ffp-contract=off mirrors Rust, which never contracts a*b+c into an FMA.
+ */
+#include "geo_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* robust 1.1.0 `orient2d` (a port of Shewchuk's predicates.c) — recalled.                      */
+/* Reference call sites: geo's RobustKernel, reached from spatial_index.rs:91-135 (contains /   */
+/* intersects) and geoseries.rs:26 (convex_hull).                                               */
+/* ------------------------------------------------------------------------------------------- */
+#define OG_EPS 1.1102230246251565e-16 /* 2^-53 */
+static const double SPLITTER = 134217729.0; /* 2^27 + 1 */
+static const double RESULTERRBOUND = (3.0 + 8.0 * OG_EPS) * OG_EPS;
+static const double CCWERRBOUND_A = (3.0 + 16.0 * OG_EPS) * OG_EPS;
+static const double CCWERRBOUND_B = (2.0 + 12.0 * OG_EPS) * OG_EPS;
+static const double CCWERRBOUND_C = (9.0 + 64.0 * OG_EPS) * OG_EPS * OG_EPS;
+
+static int64_t g_adapt_calls = 0;
+
+static inline void two_sum(double a, double b, double *x, double *y) {
+    double s = a + b;
+    double bvirt = s - a;
+    double avirt = s - bvirt;
+    double bround = b - bvirt;
+    double around = a - avirt;
+    *x = s;
+    *y = around + bround;
+}
+static inline void fast_two_sum(double a, double b, double *x, double *y) {
+    double s = a + b;
+    double bvirt = s - a;
+    *x = s;
+    *y = b - bvirt;
+}
+static inline double two_diff_tail(double a, double b, double x) {
+    double bvirt = a - x;
+    double avirt = x + bvirt;
+    double bround = bvirt - b;
+    double around = a - avirt;
+    return around + bround;
+}
+static inline void two_diff(double a, double b, double *x, double *y) {
+    double d = a - b;
+    *x = d;
+    *y = two_diff_tail(a, b, d);
+}
+static inline void split(double a, double *hi, double *lo) {
+    double c = SPLITTER * a;
+    double abig = c - a;
+    *hi = c - abig;
+    *lo = a - *hi;
+}
+static inline void two_product(double a, double b, double *x, double *y) {
+    double p = a * b;
+    double ahi, alo, bhi, blo;
+    split(a, &ahi, &alo);
+    split(b, &bhi, &blo);
+    double err1 = p - (ahi * bhi);
+    double err2 = err1 - (alo * bhi);
+    double err3 = err2 - (ahi * blo);
+    *x = p;
+    *y = (alo * blo) - err3;
+}
+/* (a1,a0) - (b1,b0) -> x[3..0] */
+static inline void two_two_diff(double a1, double a0, double b1, double b0, double x[4]) {
+    double i, j, z, t;
+    /* Two_One_Diff(a1, a0, b0, j, z, x0) */
+    two_diff(a0, b0, &i, &x[0]);
+    two_sum(a1, i, &j, &z);
+    /* Two_One_Diff(j, z, b1, x3, x2, x1) */
+    two_diff(z, b1, &i, &x[1]);
+    two_sum(j, i, &x[3], &t);
+    x[2] = t;
+}
+static int fast_expansion_sum_zeroelim(int elen, const double *e, int flen, const double *f, double *h) {
+    double Q, Qnew, hh;
+    int eindex = 0, findex = 0, hindex = 0;
+    double enow = e[0], fnow = f[0];
+    if ((fnow > enow) == (fnow > -enow)) {
+        Q = enow;
+        ++eindex;
+        enow = eindex < elen ? e[eindex] : 0.0;
+    } else {
+        Q = fnow;
+        ++findex;
+        fnow = findex < flen ? f[findex] : 0.0;
+    }
+    if ((eindex < elen) && (findex < flen)) {
+        if ((fnow > enow) == (fnow > -enow)) {
+            fast_two_sum(enow, Q, &Qnew, &hh);
+            ++eindex;
+            enow = eindex < elen ? e[eindex] : 0.0;
+        } else {
+            fast_two_sum(fnow, Q, &Qnew, &hh);
+            ++findex;
+            fnow = findex < flen ? f[findex] : 0.0;
+        }
+        Q = Qnew;
+        if (hh != 0.0) h[hindex++] = hh;
+        while ((eindex < elen) && (findex < flen)) {
+            if ((fnow > enow) == (fnow > -enow)) {
+                two_sum(Q, enow, &Qnew, &hh);
+                ++eindex;
+                enow = eindex < elen ? e[eindex] : 0.0;
+            } else {
+                two_sum(Q, fnow, &Qnew, &hh);
+                ++findex;
+                fnow = findex < flen ? f[findex] : 0.0;
+            }
+            Q = Qnew;
+            if (hh != 0.0) h[hindex++] = hh;
+        }
+    }
+    while (eindex < elen) {
+        two_sum(Q, enow, &Qnew, &hh);
+        ++eindex;
+        enow = eindex < elen ? e[eindex] : 0.0;
+        Q = Qnew;
+        if (hh != 0.0) h[hindex++] = hh;
+    }
+    while (findex < flen) {
+        two_sum(Q, fnow, &Qnew, &hh);
+        ++findex;
+        fnow = findex < flen ? f[findex] : 0.0;
+        Q = Qnew;
+        if (hh != 0.0) h[hindex++] = hh;
+    }
+    if ((Q != 0.0) || (hindex == 0)) h[hindex++] = Q;
+    return hindex;
+}
+
+static double orient2d_adapt(double ax, double ay, double bx, double by, double cx, double cy, double detsum) {
+    double acx = ax - cx, bcx = bx - cx, acy = ay - cy, bcy = by - cy;
+    double detleft, detlefttail, detright, detrighttail;
+    double B[4], u[4], C1[8], C2[12], D[16];
+    two_product(acx, bcy, &detleft, &detlefttail);
+    two_product(acy, bcx, &detright, &detrighttail);
+    two_two_diff(detleft, detlefttail, detright, detrighttail, B);
+    double det = B[0] + B[1] + B[2] + B[3];
+    double errbound = CCWERRBOUND_B * detsum;
+    if ((det >= errbound) || (-det >= errbound)) return det;
+
+    double acxtail = two_diff_tail(ax, cx, acx);
+    double bcxtail = two_diff_tail(bx, cx, bcx);
+    double acytail = two_diff_tail(ay, cy, acy);
+    double bcytail = two_diff_tail(by, cy, bcy);
+    if ((acxtail == 0.0) && (acytail == 0.0) && (bcxtail == 0.0) && (bcytail == 0.0)) return det;
+
+    errbound = CCWERRBOUND_C * detsum + RESULTERRBOUND * fabs(det);
+    det += (acx * bcytail + bcy * acxtail) - (acy * bcxtail + bcx * acytail);
+    if ((det >= errbound) || (-det >= errbound)) return det;
+
+    double s1, s0, t1, t0;
+    two_product(acxtail, bcy, &s1, &s0);
+    two_product(acytail, bcx, &t1, &t0);
+    two_two_diff(s1, s0, t1, t0, u);
+    int c1len = fast_expansion_sum_zeroelim(4, B, 4, u, C1);
+
+    two_product(acx, bcytail, &s1, &s0);
+    two_product(acy, bcxtail, &t1, &t0);
+    two_two_diff(s1, s0, t1, t0, u);
+    int c2len = fast_expansion_sum_zeroelim(c1len, C1, 4, u, C2);
+
+    two_product(acxtail, bcytail, &s1, &s0);
+    two_product(acytail, bcxtail, &t1, &t0);
+    two_two_diff(s1, s0, t1, t0, u);
+    int dlen = fast_expansion_sum_zeroelim(c2len, C2, 4, u, D);
+    return D[dlen - 1];
+}
+
+double og_orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
+    double detleft = (ax - cx) * (by - cy);
+    double detright = (ay - cy) * (bx - cx);
+    double det = detleft - detright;
+    double detsum;
+    if (detleft > 0.0) {
+        if (detright <= 0.0) return det;
+        detsum = detleft + detright;
+    } else if (detleft < 0.0) {
+        if (detright >= 0.0) return det;
+        detsum = -detleft - detright;
+    } else {
+        return det;
+    }
+    double errbound = CCWERRBOUND_A * detsum;
+    if ((det >= errbound) || (-det >= errbound)) return det;
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    g_adapt_calls++;
+    return orient2d_adapt(ax, ay, bx, by, cx, cy, detsum);
+}
+int64_t og_orient2d_adapt_calls(void) { return g_adapt_calls; }
+
+/* geo Orientation: +1 CounterClockwise, -1 Clockwise, 0 Collinear */
+static inline int orient_sign(const double *a, const double *b, const double *c) {
+    double d = og_orient2d(a[0], a[1], b[0], b[1], c[0], c[1]);
+    return (d > 0.0) - (d < 0.0);
+}
+
+static int resolve_threads(int threads) {
+#ifdef _OPENMP
+    if (threads <= 0) return omp_get_max_threads();
+    return threads;
+#else
+    (void)threads;
+    return 1;
+#endif
+}
+int og_max_threads(void) { return resolve_threads(0); }
+
+static inline int is_valid(const og_array *a, int64_t i) {
+    return a->valid == NULL || ((a->valid[i >> 3] >> (i & 7)) & 1);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* affine — GeoSeries::affine_transform geoseries.rs:11-12 ; geo AffineTransform::apply recalled */
+/* ------------------------------------------------------------------------------------------- */
+void og_affine_transform(const double *xy, int64_t n, double a, double b, double xoff, double d, double e,
+                         double yoff, double *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        out[2 * i] = a * x + b * y + xoff;
+        out[2 * i + 1] = d * x + e * y + yoff;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* area — GeoSeries::area geoseries.rs:14-16 ; geo algorithm/area.rs recalled                     */
+/* ------------------------------------------------------------------------------------------- */
+static double twice_signed_ring_area(const double *xy, int64_t n) {
+    if (n < 3) return 0.0;
+    if (xy[0] != xy[2 * (n - 1)] || xy[1] != xy[2 * (n - 1) + 1]) return 0.0;
+    double sx = xy[0], sy = xy[1];
+    double tmp = 0.0;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        double x0 = xy[2 * i] - sx, y0 = xy[2 * i + 1] - sy;
+        double x1 = xy[2 * i + 2] - sx, y1 = xy[2 * i + 3] - sy;
+        tmp = tmp + (x0 * y1 - y0 * x1);
+    }
+    return tmp;
+}
+static inline double ring_area(const double *xy, int64_t n) { return twice_signed_ring_area(xy, n) / 2.0; }
+
+/* Polygon::signed_area over rings [r0, r1) */
+static double polygon_signed_area(const og_array *a, int64_t r0, int64_t r1) {
+    if (r1 <= r0) return 0.0;
+    const int64_t *ro = a->ring_off;
+    double area = ring_area(a->xy + 2 * ro[r0], ro[r0 + 1] - ro[r0]);
+    int neg = area < 0.0;
+    double tot = fabs(area);
+    for (int64_t r = r0 + 1; r < r1; ++r) tot = tot - fabs(ring_area(a->xy + 2 * ro[r], ro[r + 1] - ro[r]));
+    return neg ? -tot : tot;
+}
+
+void og_area(const og_array *a, double *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t i = 0; i < a->n; ++i) {
+        double v = 0.0;
+        if (a->type == OG_POLYGON) {
+            v = fabs(polygon_signed_area(a, a->geom_off[i], a->geom_off[i + 1]));
+        } else if (a->type == OG_MULTIPOLYGON) {
+            for (int64_t p = a->geom_off[i]; p < a->geom_off[i + 1]; ++p)
+                v = v + fabs(polygon_signed_area(a, a->part_off[p], a->part_off[p + 1]));
+        }
+        out[i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* centroid — GeoSeries::centroid geoseries.rs:18-21 ; geo algorithm/centroid.rs recalled         */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int dim; /* -1 none (Empty), 0,1,2 */
+    double w, ax, ay;
+} wc_t;
+
+static void wc_add(wc_t *s, wc_t b) { /* add_weighted_centroid + WeightedCentroid::add_assign */
+    if (b.dim < 0) return;
+    if (s->dim < 0) {
+        *s = b;
+        return;
+    }
+    if (s->dim < b.dim) {
+        *s = b;
+    } else if (s->dim == b.dim) {
+        s->ax = s->ax + b.ax;
+        s->ay = s->ay + b.ay;
+        s->w = s->w + b.w;
+    }
+}
+static void wc_add_centroid(wc_t *s, int dim, double cx, double cy, double w) {
+    wc_t b = {dim, w, cx * w, cy * w};
+    wc_add(s, b);
+}
+static void wc_add_line(wc_t *s, const double *p0, const double *p1) {
+    if (p0[0] == p1[0] && p0[1] == p1[1]) {
+        wc_add_centroid(s, 0, p0[0], p0[1], 1.0);
+    } else {
+        double len = hypot(p1[0] - p0[0], p1[1] - p0[1]);
+        wc_add_centroid(s, 1, (p1[0] + p0[0]) / 2.0, (p1[1] + p0[1]) / 2.0, len);
+    }
+}
+static void wc_add_line_string(wc_t *s, const double *xy, int64_t n) {
+    if (s->dim > 1) return;
+    if (n == 1) {
+        wc_add_centroid(s, 0, xy[0], xy[1], 1.0);
+        return;
+    }
+    for (int64_t i = 0; i + 1 < n; ++i) wc_add_line(s, xy + 2 * i, xy + 2 * i + 2);
+}
+static void wc_add_ring(wc_t *s, const double *xy, int64_t n) {
+    double area = ring_area(xy, n);
+    if (area == 0.0) {
+        if (n == 0) return;
+        if (n == 1) {
+            wc_add_centroid(s, 0, xy[0], xy[1], 1.0);
+            return;
+        }
+        wc_add_line_string(s, xy, n);
+        return;
+    }
+    double sx = xy[0], sy = xy[1];
+    double accx = 0.0, accy = 0.0;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        double x0 = xy[2 * i] - sx, y0 = xy[2 * i + 1] - sy;
+        double x1 = xy[2 * i + 2] - sx, y1 = xy[2 * i + 3] - sy;
+        double tmp = x0 * y1 - y0 * x1;
+        accx = accx + (x1 + x0) * tmp;
+        accy = accy + (y1 + y0) * tmp;
+    }
+    double cx = accx / (6.0 * area) + sx;
+    double cy = accy / (6.0 * area) + sy;
+    wc_add_centroid(s, 2, cx, cy, fabs(area));
+}
+static void wc_add_polygon(wc_t *s, const og_array *a, int64_t r0, int64_t r1) {
+    if (r1 <= r0) return;
+    const int64_t *ro = a->ring_off;
+    wc_t ext = {-1, 0, 0, 0}, itr = {-1, 0, 0, 0};
+    wc_add_ring(&ext, a->xy + 2 * ro[r0], ro[r0 + 1] - ro[r0]);
+    for (int64_t r = r0 + 1; r < r1; ++r) wc_add_ring(&itr, a->xy + 2 * ro[r], ro[r + 1] - ro[r]);
+    if (ext.dim >= 0) {
+        wc_t poly = ext;
+        if (itr.dim >= 0) {
+            if (poly.dim == itr.dim) { /* WeightedCentroid::sub_assign */
+                poly.ax = poly.ax - itr.ax;
+                poly.ay = poly.ay - itr.ay;
+                poly.w = poly.w - itr.w;
+            }
+            if (poly.w == 0.0) {
+                wc_add_line_string(s, a->xy + 2 * ro[r0], ro[r0 + 1] - ro[r0]);
+                return;
+            }
+        }
+        wc_add(s, poly);
+    }
+}
+
+void og_centroid(const og_array *a, double *out_xy, uint8_t *out_valid, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t i = 0; i < a->n; ++i) {
+        wc_t s = {-1, 0, 0, 0};
+        int ok = is_valid(a, i);
+        if (ok) {
+            switch (a->type) {
+            case OG_POINT:
+                /* geo: Point::centroid == self; an empty (NaN) point has no centroid */
+                if (!(isnan(a->xy[2 * i]) && isnan(a->xy[2 * i + 1]))) wc_add_centroid(&s, 0, a->xy[2 * i], a->xy[2 * i + 1], 1.0);
+                break;
+            case OG_MULTIPOINT:
+                for (int64_t c = a->geom_off[i]; c < a->geom_off[i + 1]; ++c)
+                    wc_add_centroid(&s, 0, a->xy[2 * c], a->xy[2 * c + 1], 1.0);
+                break;
+            case OG_LINESTRING:
+                wc_add_line_string(&s, a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i]);
+                break;
+            case OG_MULTILINESTRING:
+                for (int64_t l = a->geom_off[i]; l < a->geom_off[i + 1]; ++l)
+                    wc_add_line_string(&s, a->xy + 2 * a->ring_off[l], a->ring_off[l + 1] - a->ring_off[l]);
+                break;
+            case OG_POLYGON:
+                wc_add_polygon(&s, a, a->geom_off[i], a->geom_off[i + 1]);
+                break;
+            case OG_MULTIPOLYGON:
+                for (int64_t p = a->geom_off[i]; p < a->geom_off[i + 1]; ++p)
+                    wc_add_polygon(&s, a, a->part_off[p], a->part_off[p + 1]);
+                break;
+            default:
+                break;
+            }
+        }
+        if (s.dim >= 0) {
+            if (a->type == OG_POINT) { /* exact pass-through, no w*x/w round trip needed: 1.0 weights are exact */
+                out_xy[2 * i] = s.ax / s.w;
+                out_xy[2 * i + 1] = s.ay / s.w;
+            } else {
+                out_xy[2 * i] = s.ax / s.w;
+                out_xy[2 * i + 1] = s.ay / s.w;
+            }
+            out_valid[i] = 1;
+        } else {
+            out_xy[2 * i] = NAN;
+            out_xy[2 * i + 1] = NAN;
+            out_valid[i] = 0;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* envelope / length — geoseries.rs:28-41 ; geo bounding_rect.rs, euclidean_length.rs recalled    */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int has;
+    double x0, y0, x1, y1;
+} bb_t;
+static inline void bb_add(bb_t *b, const double *xy, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        double px = xy[2 * i], py = xy[2 * i + 1];
+        if (!b->has) {
+            b->has = 1;
+            b->x0 = b->x1 = px;
+            b->y0 = b->y1 = py;
+            continue;
+        }
+        if (px > b->x1) b->x1 = px;
+        else if (px < b->x0) b->x0 = px;
+        if (py > b->y1) b->y1 = py;
+        else if (py < b->y0) b->y0 = py;
+    }
+}
+static bb_t geom_bbox(const og_array *a, int64_t i) {
+    bb_t b = {0, 0, 0, 0, 0};
+    const int64_t *go = a->geom_off, *ro = a->ring_off, *po = a->part_off;
+    switch (a->type) {
+    case OG_POINT:
+        if (!(isnan(a->xy[2 * i]) && isnan(a->xy[2 * i + 1]))) bb_add(&b, a->xy + 2 * i, 1);
+        break;
+    case OG_LINESTRING:
+    case OG_MULTIPOINT:
+        bb_add(&b, a->xy + 2 * go[i], go[i + 1] - go[i]);
+        break;
+    case OG_MULTILINESTRING:
+        for (int64_t l = go[i]; l < go[i + 1]; ++l) bb_add(&b, a->xy + 2 * ro[l], ro[l + 1] - ro[l]);
+        break;
+    case OG_POLYGON: /* exterior only */
+        if (go[i + 1] > go[i]) bb_add(&b, a->xy + 2 * ro[go[i]], ro[go[i] + 1] - ro[go[i]]);
+        break;
+    case OG_MULTIPOLYGON:
+        for (int64_t p = go[i]; p < go[i + 1]; ++p)
+            if (po[p + 1] > po[p]) bb_add(&b, a->xy + 2 * ro[po[p]], ro[po[p] + 1] - ro[po[p]]);
+        break;
+    default:
+        break;
+    }
+    return b;
+}
+void og_envelope(const og_array *a, double *out4, uint8_t *out_valid, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t i = 0; i < a->n; ++i) {
+        bb_t b = {0, 0, 0, 0, 0};
+        if (is_valid(a, i)) b = geom_bbox(a, i);
+        out_valid[i] = (uint8_t)b.has;
+        out4[4 * i] = b.has ? b.x0 : NAN;
+        out4[4 * i + 1] = b.has ? b.y0 : NAN;
+        out4[4 * i + 2] = b.has ? b.x1 : NAN;
+        out4[4 * i + 3] = b.has ? b.y1 : NAN;
+    }
+}
+static double ls_length(const double *xy, int64_t n) {
+    double s = 0.0;
+    for (int64_t i = 0; i + 1 < n; ++i) s = s + hypot(xy[2 * i + 2] - xy[2 * i], xy[2 * i + 3] - xy[2 * i + 1]);
+    return s;
+}
+void og_euclidean_length(const og_array *a, double *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    const int64_t *go = a->geom_off, *ro = a->ring_off, *po = a->part_off;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t i = 0; i < a->n; ++i) {
+        double v = 0.0;
+        switch (a->type) {
+        case OG_LINESTRING:
+            v = ls_length(a->xy + 2 * go[i], go[i + 1] - go[i]);
+            break;
+        case OG_MULTILINESTRING:
+            for (int64_t l = go[i]; l < go[i + 1]; ++l) v = v + ls_length(a->xy + 2 * ro[l], ro[l + 1] - ro[l]);
+            break;
+        case OG_POLYGON: /* geoseries.rs:35-41: "for Polygon it's the length of the exterior ring" */
+            if (go[i + 1] > go[i]) v = ls_length(a->xy + 2 * ro[go[i]], ro[go[i] + 1] - ro[go[i]]);
+            break;
+        case OG_MULTIPOLYGON:
+            for (int64_t p = go[i]; p < go[i + 1]; ++p)
+                if (po[p + 1] > po[p]) v = v + ls_length(a->xy + 2 * ro[po[p]], ro[po[p] + 1] - ro[po[p]]);
+            break;
+        default:
+            break;
+        }
+        out[i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* contains — spatial_index.rs:89-96 `poly.contains(point)` ; geo coordinate_position.rs recalled */
+/* ------------------------------------------------------------------------------------------- */
+static inline int value_in_between(double v, double b1, double b2) {
+    if (b1 < b2) return v >= b1 && v <= b2;
+    return v >= b2 && v <= b1;
+}
+static inline int point_in_rect(const double *v, const double *b1, const double *b2) {
+    return value_in_between(v[0], b1[0], b2[0]) && value_in_between(v[1], b1[1], b2[1]);
+}
+enum { POS_OUTSIDE = 0, POS_BOUNDARY = 1, POS_INSIDE = 2 };
+
+/* coord_pos_relative_to_ring.  Rings in GeoArrow are explicitly closed; geo's Polygon::new closes an
+ * open ring by appending the first coord, which `closing` emulates. */
+static int coord_pos_ring(double px, double py, const double *xy, int64_t n) {
+    if (n == 0) return POS_OUTSIDE;
+    if (n == 1) return (px == xy[0] && py == xy[1]) ? POS_BOUNDARY : POS_OUTSIDE;
+    int closing = !(xy[0] == xy[2 * (n - 1)] && xy[1] == xy[2 * (n - 1) + 1]);
+    int64_t nseg = n - 1 + closing;
+    int wn = 0;
+    double p[2] = {px, py};
+    for (int64_t i = 0; i < nseg; ++i) {
+        const double *s = xy + 2 * i;
+        const double *e = (i + 1 < n) ? xy + 2 * (i + 1) : xy;
+        if (s[1] <= py) {
+            if (e[1] >= py) {
+                int o = orient_sign(s, e, p);
+                if (o > 0 && e[1] != py) wn += 1;
+                else if (o == 0 && value_in_between(px, s[0], e[0])) return POS_BOUNDARY;
+            }
+        } else if (e[1] <= py) {
+            int o = orient_sign(s, e, p);
+            if (o < 0) wn -= 1;
+            else if (o == 0 && value_in_between(px, s[0], e[0])) return POS_BOUNDARY;
+        }
+    }
+    return wn == 0 ? POS_OUTSIDE : POS_INSIDE;
+}
+/* Polygon::calculate_coordinate_position over rings [r0,r1) */
+static void polygon_coord_pos(const og_array *a, int64_t r0, int64_t r1, double px, double py, int *is_inside,
+                              int64_t *boundary_count) {
+    const int64_t *ro = a->ring_off;
+    if (r1 <= r0) return;
+    if (ro[r0 + 1] - ro[r0] == 0) return;
+    int pos = coord_pos_ring(px, py, a->xy + 2 * ro[r0], ro[r0 + 1] - ro[r0]);
+    if (pos == POS_OUTSIDE) return;
+    if (pos == POS_BOUNDARY) {
+        *boundary_count += 1;
+        return;
+    }
+    for (int64_t r = r0 + 1; r < r1; ++r) {
+        int hp = coord_pos_ring(px, py, a->xy + 2 * ro[r], ro[r + 1] - ro[r]);
+        if (hp == POS_BOUNDARY) {
+            *boundary_count += 1;
+            return;
+        }
+        if (hp == POS_INSIDE) return;
+    }
+    *is_inside = 1;
+}
+int og_coord_position(const og_array *a, int64_t i, double px, double py) {
+    int inside = 0;
+    int64_t bc = 0;
+    if (a->type == OG_POLYGON) {
+        polygon_coord_pos(a, a->geom_off[i], a->geom_off[i + 1], px, py, &inside, &bc);
+    } else if (a->type == OG_MULTIPOLYGON) {
+        for (int64_t p = a->geom_off[i]; p < a->geom_off[i + 1]; ++p)
+            polygon_coord_pos(a, a->part_off[p], a->part_off[p + 1], px, py, &inside, &bc);
+    }
+    if (bc % 2 == 1) return POS_BOUNDARY;
+    return inside ? POS_INSIDE : POS_OUTSIDE;
+}
+int og_contains_point(const og_array *a, int64_t i, double px, double py) {
+    if (!is_valid(a, i)) return 0;
+    if (a->type == OG_POLYGON) return og_coord_position(a, i, px, py) == POS_INSIDE;
+    if (a->type == OG_MULTIPOLYGON) { /* MultiPolygon::contains(coord) = any polygon contains */
+        for (int64_t p = a->geom_off[i]; p < a->geom_off[i + 1]; ++p) {
+            int inside = 0;
+            int64_t bc = 0;
+            polygon_coord_pos(a, a->part_off[p], a->part_off[p + 1], px, py, &inside, &bc);
+            if (bc % 2 == 0 && inside) return 1;
+        }
+    }
+    return 0;
+}
+
+/* broadcast join.  The grid is only a candidate filter (closed-interval bbox overlap like rstar's
+ * AABB test, spatial_index.rs:74-76, 289); the exact test decides. */
+void og_contains_join(const og_array *polys, const double *pts, int64_t n_pts, int32_t *first_id, int32_t *count,
+                      int use_grid, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    int64_t m = polys->n;
+    double *bb = (double *)malloc(sizeof(double) * 4 * (size_t)(m > 0 ? m : 1));
+    uint8_t *bbv = (uint8_t *)malloc((size_t)(m > 0 ? m : 1));
+    double gx0 = INFINITY, gy0 = INFINITY, gx1 = -INFINITY, gy1 = -INFINITY;
+    for (int64_t j = 0; j < m; ++j) {
+        bb_t b = {0, 0, 0, 0, 0};
+        if (is_valid(polys, j)) b = geom_bbox(polys, j);
+        bbv[j] = (uint8_t)b.has;
+        bb[4 * j] = b.x0, bb[4 * j + 1] = b.y0, bb[4 * j + 2] = b.x1, bb[4 * j + 3] = b.y1;
+        if (b.has) {
+            if (b.x0 < gx0) gx0 = b.x0;
+            if (b.y0 < gy0) gy0 = b.y0;
+            if (b.x1 > gx1) gx1 = b.x1;
+            if (b.y1 > gy1) gy1 = b.y1;
+        }
+    }
+    int G = 1;
+    int64_t *cell_start = NULL;
+    int32_t *cell_items = NULL;
+    double inv_w = 0, inv_h = 0;
+    if (use_grid && m > 0 && gx1 >= gx0) {
+        G = (int)ceil(sqrt((double)m));
+        if (G < 1) G = 1;
+        if (G > 2048) G = 2048;
+        inv_w = (gx1 > gx0) ? G / (gx1 - gx0) : 0.0;
+        inv_h = (gy1 > gy0) ? G / (gy1 - gy0) : 0.0;
+        cell_start = (int64_t *)calloc((size_t)G * G + 1, sizeof(int64_t));
+#define CELL(v, lo, inv) ({ double t_ = floor(((v) - (lo)) * (inv)); int c_ = t_ < 0 ? 0 : (t_ >= G ? G - 1 : (int)t_); c_; })
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                int64_t acc = 0;
+                for (int64_t c = 0; c < (int64_t)G * G; ++c) {
+                    int64_t t = cell_start[c];
+                    cell_start[c] = acc;
+                    acc += t;
+                }
+                cell_start[(int64_t)G * G] = acc;
+                cell_items = (int32_t *)malloc(sizeof(int32_t) * (size_t)(acc > 0 ? acc : 1));
+            }
+            int64_t *fill = NULL;
+            if (pass == 1) {
+                fill = (int64_t *)malloc(sizeof(int64_t) * (size_t)G * G);
+                memcpy(fill, cell_start, sizeof(int64_t) * (size_t)G * G);
+            }
+            for (int64_t j = 0; j < m; ++j) {
+                if (!bbv[j]) continue;
+                int cx0 = CELL(bb[4 * j], gx0, inv_w), cx1 = CELL(bb[4 * j + 2], gx0, inv_w);
+                int cy0 = CELL(bb[4 * j + 1], gy0, inv_h), cy1 = CELL(bb[4 * j + 3], gy0, inv_h);
+                for (int cy = cy0; cy <= cy1; ++cy)
+                    for (int cx = cx0; cx <= cx1; ++cx) {
+                        int64_t c = (int64_t)cy * G + cx;
+                        if (pass == 0) cell_start[c]++;
+                        else cell_items[fill[c]++] = (int32_t)j;
+                    }
+            }
+            free(fill);
+        }
+    }
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t p = 0; p < n_pts; ++p) {
+        double px = pts[2 * p], py = pts[2 * p + 1];
+        int32_t first = -1, cnt = 0;
+        if (cell_start) {
+            if (px >= gx0 && px <= gx1 && py >= gy0 && py <= gy1) {
+                int cx = CELL(px, gx0, inv_w), cy = CELL(py, gy0, inv_h);
+                int64_t c = (int64_t)cy * G + cx;
+                for (int64_t k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                    int32_t j = cell_items[k];
+                    if (px < bb[4 * j] || px > bb[4 * j + 2] || py < bb[4 * j + 1] || py > bb[4 * j + 3]) continue;
+                    if (og_contains_point(polys, j, px, py)) {
+                        if (first < 0 || j < first) first = j;
+                        cnt++;
+                    }
+                }
+            }
+        } else {
+            for (int64_t j = 0; j < m; ++j) {
+                if (!bbv[j]) continue;
+                if (og_contains_point(polys, j, px, py)) {
+                    if (first < 0) first = (int32_t)j;
+                    cnt++;
+                }
+            }
+        }
+        first_id[p] = first;
+        if (count) count[p] = cnt;
+    }
+    free(bb);
+    free(bbv);
+    free(cell_start);
+    free(cell_items);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* intersects — spatial_index.rs:102-104 semantics donor ; geo intersects/{line,line_string}.rs   */
+/* ------------------------------------------------------------------------------------------- */
+static int line_intersects_coord(const double *s, const double *e, const double *c) {
+    return orient_sign(s, e, c) == 0 && point_in_rect(c, s, e);
+}
+/* impl Intersects<Line> for Line: `self`=(s0,e0), `line`=(s1,e1) */
+static int line_intersects_line(const double *s0, const double *e0, const double *s1, const double *e1) {
+    if (s0[0] == e0[0] && s0[1] == e0[1]) return line_intersects_coord(s1, e1, s0);
+    int c11 = orient_sign(s0, e0, s1);
+    int c12 = orient_sign(s0, e0, e1);
+    if (c11 != c12) {
+        int c21 = orient_sign(s1, e1, s0);
+        int c22 = orient_sign(s1, e1, e0);
+        return c21 != c22;
+    } else if (c11 == 0) {
+        return point_in_rect(s1, s0, e0) || point_in_rect(e1, s0, e0) || point_in_rect(e0, s1, e1) ||
+               point_in_rect(e0, s1, e1);
+    }
+    return 0;
+}
+static int ls_bbox(const double *xy, int64_t n, double *b) {
+    bb_t t = {0, 0, 0, 0, 0};
+    bb_add(&t, xy, n);
+    b[0] = t.x0, b[1] = t.y0, b[2] = t.x1, b[3] = t.y1;
+    return t.has;
+}
+static int ls_intersects_ls(const double *a, int64_t na, const double *b, int64_t nb) {
+    double ba[4], bbx[4];
+    int ha = ls_bbox(a, na, ba), hb = ls_bbox(b, nb, bbx);
+    /* has_disjoint_bboxes: only when both have a bbox */
+    if (ha && hb) {
+        if (ba[0] > bbx[2] || bbx[0] > ba[2] || ba[1] > bbx[3] || bbx[1] > ba[3]) return 0;
+    }
+    for (int64_t i = 0; i + 1 < na; ++i)
+        for (int64_t j = 0; j + 1 < nb; ++j)
+            if (line_intersects_line(b + 2 * j, b + 2 * j + 2, a + 2 * i, a + 2 * i + 2)) return 1;
+    return 0;
+}
+void og_intersects_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
+    for (int64_t i = 0; i < a->n; ++i) {
+        uint8_t r = 0;
+        if (is_valid(a, i) && is_valid(b, i) && a->type == OG_LINESTRING && b->type == OG_LINESTRING) {
+            r = (uint8_t)ls_intersects_ls(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i],
+                                         b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i]);
+        }
+        out[i] = r;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* distance — GeoSeries::distance geoseries.rs:141-146 ; geo euclidean_distance.rs +              */
+/* geo-types private_utils.rs recalled                                                          */
+/* ------------------------------------------------------------------------------------------- */
+static inline double pt_dist(const double *a, const double *b) { return hypot(b[0] - a[0], b[1] - a[1]); }
+static double line_segment_distance(const double *p, const double *s, const double *e) {
+    if (s[0] == e[0] && s[1] == e[1]) return pt_dist(p, s);
+    double dx = e[0] - s[0], dy = e[1] - s[1];
+    double d2 = dx * dx + dy * dy;
+    double r = ((p[0] - s[0]) * dx + (p[1] - s[1]) * dy) / d2;
+    if (r <= 0.0) return pt_dist(p, s);
+    if (r >= 1.0) return pt_dist(p, e);
+    double sv = ((s[1] - p[1]) * dx - (s[0] - p[0]) * dy) / d2;
+    return fabs(sv) * hypot(dx, dy);
+}
+/* geo-types private_utils::line_string_contains_point (inexact, epsilon based) */
+static int line_string_contains_point(const double *xy, int64_t n, const double *p) {
+    if (n == 0) return 0;
+    if (n == 1) {
+        float d = (float)pt_dist(xy, p);
+        return d <= 1.1920929e-07f; /* approx::relative_eq!(d, 0.0) on f32 */
+    }
+    for (int64_t i = 0; i < n; ++i)
+        if (xy[2 * i] == p[0] && xy[2 * i + 1] == p[1]) return 1;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const double *s = xy + 2 * i, *e = xy + 2 * i + 2;
+        double dx = e[0] - s[0], dy = e[1] - s[1];
+        int hx = dx != 0.0, hy = dy != 0.0;
+        double tx = hx ? (p[0] - s[0]) / dx : 0.0;
+        double ty = hy ? (p[1] - s[1]) / dy : 0.0;
+        int c;
+        if (!hx && !hy) c = (p[0] == s[0] && p[1] == s[1]);
+        else if (hx && !hy) c = (p[1] == s[1] && 0.0 <= tx && tx <= 1.0);
+        else if (!hx && hy) c = (p[0] == s[0] && 0.0 <= ty && ty <= 1.0);
+        else c = (fabs(tx - ty) <= 2.220446049250313e-16 && 0.0 <= tx && tx <= 1.0);
+        if (c) return 1;
+    }
+    return 0;
+}
+static double point_ls_distance(const double *p, const double *xy, int64_t n) {
+    if (line_string_contains_point(xy, n, p) || n == 0) return 0.0;
+    double acc = 1.7976931348623157e308;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        double v = line_segment_distance(p, xy + 2 * i, xy + 2 * i + 2);
+        acc = fmin(acc, v);
+    }
+    return acc;
+}
+static double ls_ls_distance(const double *a, int64_t na, const double *b, int64_t nb, int *ok) {
+    if (ls_intersects_ls(a, na, b, nb)) return 0.0;
+    if (na < 2 || nb < 2) { /* reference: nearest_neighbor(..).unwrap() panics on an empty tree */
+        *ok = 0;
+        return NAN;
+    }
+    double m1 = 1.7976931348623157e308, m2 = 1.7976931348623157e308;
+    for (int64_t j = 0; j < nb; ++j) { /* every point of B against lines of A */
+        double best = 1.7976931348623157e308;
+        for (int64_t i = 0; i + 1 < na; ++i) best = fmin(best, line_segment_distance(b + 2 * j, a + 2 * i, a + 2 * i + 2));
+        m1 = fmin(m1, best);
+    }
+    for (int64_t i = 0; i < na; ++i) {
+        double best = 1.7976931348623157e308;
+        for (int64_t j = 0; j + 1 < nb; ++j) best = fmin(best, line_segment_distance(a + 2 * i, b + 2 * j, b + 2 * j + 2));
+        m2 = fmin(m2, best);
+    }
+    return fmin(m1, m2);
+}
+static double point_polygon_distance(const double *p, const og_array *a, int64_t i) {
+    const int64_t *go = a->geom_off, *ro = a->ring_off;
+    int64_t r0 = go[i], r1 = go[i + 1];
+    if (r1 <= r0 || ro[r0 + 1] - ro[r0] == 0) return 0.0;
+    if (og_coord_position(a, i, p[0], p[1]) != POS_OUTSIDE) return 0.0;
+    double acc = 1.7976931348623157e308;
+    for (int64_t r = r0 + 1; r < r1; ++r) acc = fmin(acc, point_ls_distance(p, a->xy + 2 * ro[r], ro[r + 1] - ro[r]));
+    double ext = 1.7976931348623157e308;
+    const double *xy = a->xy + 2 * ro[r0];
+    for (int64_t k = 0; k + 1 < ro[r0 + 1] - ro[r0]; ++k) ext = fmin(ext, line_segment_distance(p, xy + 2 * k, xy + 2 * k + 2));
+    return fmin(acc, ext);
+}
+int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    int ta = a->type, tb = b->type;
+    int supported = (ta == OG_POINT || ta == OG_LINESTRING || ta == OG_POLYGON) &&
+                    (tb == OG_POINT || tb == OG_LINESTRING || tb == OG_POLYGON) &&
+                    !(ta == OG_POLYGON && tb != OG_POINT) && !(tb == OG_POLYGON && ta != OG_POINT);
+    if (!supported || a->n != b->n) return -1;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
+    for (int64_t i = 0; i < a->n; ++i) {
+        double v = NAN;
+        if (is_valid(a, i) && is_valid(b, i)) {
+            int ok = 1;
+            if (ta == OG_POINT && tb == OG_POINT) v = pt_dist(a->xy + 2 * i, b->xy + 2 * i);
+            else if (ta == OG_POINT && tb == OG_LINESTRING)
+                v = point_ls_distance(a->xy + 2 * i, b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i]);
+            else if (ta == OG_LINESTRING && tb == OG_POINT)
+                v = point_ls_distance(b->xy + 2 * i, a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i]);
+            else if (ta == OG_LINESTRING && tb == OG_LINESTRING)
+                v = ls_ls_distance(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i],
+                                   b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i], &ok);
+            else if (ta == OG_POINT && tb == OG_POLYGON) v = point_polygon_distance(a->xy + 2 * i, b, i);
+            else if (ta == OG_POLYGON && tb == OG_POINT) v = point_polygon_distance(b->xy + 2 * i, a, i);
+            (void)ok;
+        }
+        out[i] = v;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* convex hull — GeoSeries::convex_hull geoseries.rs:23-26 ; geo convex_hull/{mod,qhull}.rs       */
+/* recalled, including the in-place slice permutations that fix the output vertex order.        */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double x, y;
+} coord_t;
+static inline int lex_cmp(const coord_t *a, const coord_t *b) {
+    if (a->x < b->x) return -1;
+    if (a->x > b->x) return 1;
+    if (a->y < b->y) return -1;
+    if (a->y > b->y) return 1;
+    return 0;
+}
+static inline int is_ccw(coord_t a, coord_t b, coord_t c) { return og_orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
+static inline void cswap(coord_t *a, coord_t *b) {
+    coord_t t = *a;
+    *a = *b;
+    *b = t;
+}
+/* utils::partition_slice (Hoare style): returns number of elements satisfying pred, moved to front */
+static int64_t partition_ccw(coord_t *d, int64_t len, coord_t pa, coord_t pb) {
+    if (len == 0) return 0;
+    int64_t l = 0, r = len - 1;
+    for (;;) {
+        while (l < len && is_ccw(pa, pb, d[l])) l++;
+        while (r > 0 && !is_ccw(pa, pb, d[r])) r--;
+        if (l >= r) return l;
+        cswap(&d[l], &d[r]);
+    }
+}
+typedef struct {
+    coord_t *v;
+    int64_t n, cap;
+} cvec;
+static void cpush(cvec *h, coord_t c) {
+    if (h->n == h->cap) {
+        h->cap = h->cap ? h->cap * 2 : 64;
+        h->v = (coord_t *)realloc(h->v, sizeof(coord_t) * (size_t)h->cap);
+    }
+    h->v[h->n++] = c;
+}
+static void hull_set(coord_t pa, coord_t pb, coord_t *set, int64_t len, cvec *hull) {
+    if (len == 0) return;
+    if (len == 1) {
+        cpush(hull, set[0]);
+        return;
+    }
+    double ox = pa.y - pb.y, oy = pb.x - pa.x;
+    int64_t fi = 0;
+    double fv = 0;
+    for (int64_t i = 0; i < len; ++i) { /* Iterator::max_by — last maximal element wins */
+        double dx = set[i].x - pa.x, dy = set[i].y - pa.y;
+        double v = ox * dx + oy * dy;
+        if (i == 0 || !(v < fv)) {
+            fi = i;
+            fv = v;
+        }
+    }
+    cswap(&set[0], &set[fi]); /* swap_remove_to_first */
+    coord_t far = set[0];
+    set += 1;
+    len -= 1;
+    int64_t k = partition_ccw(set, len, far, pb);
+    hull_set(far, pb, set, k, hull);
+    cpush(hull, far);
+    k = partition_ccw(set, len, pa, far);
+    hull_set(pa, far, set, k, hull);
+}
+static void trivial_hull(coord_t *pts, int64_t n, cvec *hull) {
+    coord_t ls[4];
+    int64_t m = n;
+    for (int64_t i = 0; i < n; ++i) ls[i] = pts[i];
+    /* sort_unstable_by(lex_cmp) on <= 3 items */
+    for (int64_t i = 1; i < m; ++i)
+        for (int64_t j = i; j > 0 && lex_cmp(&ls[j], &ls[j - 1]) < 0; --j) cswap(&ls[j], &ls[j - 1]);
+    if (m == 3 && og_orient2d(ls[0].x, ls[0].y, ls[1].x, ls[1].y, ls[2].x, ls[2].y) == 0.0) {
+        ls[1] = ls[2];
+        m = 2;
+    }
+    if (m == 1) ls[m++] = ls[0];
+    if (m == 0) return;
+    /* close */
+    if (!(ls[0].x == ls[m - 1].x && ls[0].y == ls[m - 1].y)) ls[m++] = ls[0];
+    /* make_ccw_winding: only a closed ring with >= 4 coords has a winding order */
+    if (m >= 4) {
+        /* least index = 0 after the sort; next = 1; prev = m-2 (m-1 duplicates index 0) */
+        if (og_orient2d(ls[m - 2].x, ls[m - 2].y, ls[0].x, ls[0].y, ls[1].x, ls[1].y) < 0.0) {
+            for (int64_t i = 0, j = m - 1; i < j; ++i, --j) cswap(&ls[i], &ls[j]);
+        }
+    }
+    for (int64_t i = 0; i < m; ++i) cpush(hull, ls[i]);
+}
+static void quick_hull(coord_t *pts, int64_t n, cvec *hull) {
+    if (n < 4) {
+        trivial_hull(pts, n, hull);
+        return;
+    }
+    int64_t min_idx = 0, max_idx = 0;
+    for (int64_t i = 1; i < n; ++i) { /* utils::least_and_greatest_index: first least, first greatest */
+        if (lex_cmp(&pts[i], &pts[min_idx]) < 0) min_idx = i;
+        if (lex_cmp(&pts[i], &pts[max_idx]) > 0) max_idx = i;
+    }
+    cswap(&pts[0], &pts[min_idx]);
+    coord_t mn = pts[0];
+    pts += 1;
+    n -= 1;
+    if (max_idx == 0) max_idx = min_idx;
+    max_idx = max_idx > 0 ? max_idx - 1 : 0;
+    cswap(&pts[0], &pts[max_idx]);
+    coord_t mx = pts[0];
+    pts += 1;
+    n -= 1;
+    int64_t k = partition_ccw(pts, n, mx, mn);
+    hull_set(mx, mn, pts, k, hull);
+    cpush(hull, mx);
+    k = partition_ccw(pts, n, mn, mx);
+    hull_set(mn, mx, pts, k, hull);
+    cpush(hull, mn);
+    if (!(hull->v[0].x == hull->v[hull->n - 1].x && hull->v[0].y == hull->v[hull->n - 1].y)) cpush(hull, hull->v[0]);
+}
+/* CoordsIter::exterior_coords_iter */
+static int64_t gather_exterior(const og_array *a, int64_t i, coord_t *dst) {
+    const int64_t *go = a->geom_off, *ro = a->ring_off, *po = a->part_off;
+    int64_t n = 0;
+#define PUSH_RANGE(c0, c1)                                                                                   \
+    for (int64_t c_ = (c0); c_ < (c1); ++c_) {                                                               \
+        if (dst) { dst[n].x = a->xy[2 * c_]; dst[n].y = a->xy[2 * c_ + 1]; }                                  \
+        n++;                                                                                                 \
+    }
+    switch (a->type) {
+    case OG_POINT:
+        PUSH_RANGE(i, i + 1);
+        break;
+    case OG_LINESTRING:
+    case OG_MULTIPOINT:
+        PUSH_RANGE(go[i], go[i + 1]);
+        break;
+    case OG_MULTILINESTRING:
+        for (int64_t l = go[i]; l < go[i + 1]; ++l) PUSH_RANGE(ro[l], ro[l + 1]);
+        break;
+    case OG_POLYGON:
+        if (go[i + 1] > go[i]) PUSH_RANGE(ro[go[i]], ro[go[i] + 1]);
+        break;
+    case OG_MULTIPOLYGON:
+        for (int64_t p = go[i]; p < go[i + 1]; ++p)
+            if (po[p + 1] > po[p]) PUSH_RANGE(ro[po[p]], ro[po[p] + 1]);
+        break;
+    default:
+        break;
+    }
+    return n;
+}
+int64_t og_convex_hull_one(const og_array *a, int64_t i, double *out_xy, int64_t cap) {
+    int64_t n = gather_exterior(a, i, NULL);
+    coord_t *pts = (coord_t *)malloc(sizeof(coord_t) * (size_t)(n > 0 ? n : 1));
+    gather_exterior(a, i, pts);
+    cvec hull = {NULL, 0, 0};
+    quick_hull(pts, n, &hull);
+    int64_t m = hull.n;
+    if (out_xy)
+        for (int64_t k = 0; k < m && k < cap; ++k) {
+            out_xy[2 * k] = hull.v[k].x;
+            out_xy[2 * k + 1] = hull.v[k].y;
+        }
+    free(hull.v);
+    free(pts);
+    return m;
+}
+int64_t og_convex_hull(const og_array *a, int64_t *out_off, double *out_xy, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    int64_t n = a->n;
+    int64_t *sizes = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    if (out_xy == NULL) {
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) sizes[i] = is_valid(a, i) ? og_convex_hull_one(a, i, NULL, 0) : 0;
+        int64_t acc = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            out_off[i] = acc;
+            acc += sizes[i];
+        }
+        out_off[n] = acc;
+        free(sizes);
+        return acc;
+    }
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i)
+        if (is_valid(a, i)) og_convex_hull_one(a, i, out_xy + 2 * out_off[i], out_off[i + 1] - out_off[i]);
+    free(sizes);
+    return out_off[n];
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* synthetic data — SURVEY.md §8d RNG                                                          */
+/* ------------------------------------------------------------------------------------------- */
+double og_splitmix_u(uint64_t seed, uint64_t counter) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (counter + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (double)(z >> 11) * 0x1.0p-53;
+}
+void og_gen_uniform_points(uint64_t stream, int64_t first, int64_t n, double scale, double *out_xy) {
+    uint64_t seed = 0xB2000000ULL + stream;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t g = (uint64_t)(first + i);
+        out_xy[2 * i] = scale * og_splitmix_u(seed, g * 4ULL + 0ULL);
+        out_xy[2 * i + 1] = scale * og_splitmix_u(seed, g * 4ULL + 1ULL);
+    }
+}
