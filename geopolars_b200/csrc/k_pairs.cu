@@ -1,0 +1,472 @@
+// k_pairs.cu — row-wise binary ops: distance, intersects, contains (1:1 aligned rows).
+// Reference: GeoSeries::distance geoseries.rs:141-146 (impl :248-251 names the historical callee
+// ops::distance::euclidean_distance); intersects / contains semantics from the dead join code
+// geopolars/src/spatial_index.rs:89-137.  Arithmetic = geo 0.27 euclidean_distance.rs,
+// intersects/{line,line_string}.rs, coordinate_position.rs and geo-types private_utils.rs (recalled;
+// restated in oracle/geo_oracle.c).
+//
+// Design: one warp per row.  Both linestrings of the row are staged into shared memory with one
+// coalesced LDG.128 per lane (BASELINE config 3: 16+16 coords = 512 B per row, one warp-wide load), then
+//   intersects: lanes stride over the (na-1)*(nb-1) segment pairs; closed bbox reject (exact) before
+//               the 2-4 exact orient2d calls; warp-wide early exit with __any_sync;
+//   distance  : only if not intersecting; lanes stride over the nb*(na-1) + na*(nb-1) (vertex, segment)
+//               items, keep min SQUARED distance (no hypot/division on the endpoint cases, one division
+//               on interior projections), one sqrt after the warp min.  The cancellation-prone term
+//               (the cross product) is evaluated with exactly the reference's expression, so the result
+//               differs from geo's |s|*hypot(dx,dy) only by the last two roundings (<= 4 ulp; the stated
+//               tolerance for f64 outputs is 1e-9 relative).
+// These kernels are FP64-ALU bound, not HBM bound (~225 segment tests + ~480 distance items per 512 B).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gpl {
+
+constexpr int kPairWarps = 8;     // warps per CTA
+constexpr int kPairSmemCoords = 128;  // coords of (A,B) staged per warp; longer rows read global memory
+
+struct Coords {  // accessor over either staging area
+    const double2 *p;
+    __device__ __forceinline__ double2 operator[](int64_t i) const { return p[i]; }
+};
+
+__device__ __forceinline__ bool seg_bbox_disjoint(double2 a0, double2 a1, double2 b0, double2 b1) {
+    return fmax(a0.x, a1.x) < fmin(b0.x, b1.x) || fmax(b0.x, b1.x) < fmin(a0.x, a1.x) || fmax(a0.y, a1.y) < fmin(b0.y, b1.y) ||
+           fmax(b0.y, b1.y) < fmin(a0.y, a1.y);
+}
+__device__ __forceinline__ bool line_intersects_coord(double2 s, double2 e, double2 c) {
+    return orient_sign(s, e, c) == 0 && point_in_rect(c, s, e);
+}
+// impl Intersects<Line> for Line, self = (s0,e0), rhs = (s1,e1)
+__device__ __forceinline__ bool line_intersects_line(double2 s0, double2 e0, double2 s1, double2 e1) {
+    if (s0.x == e0.x && s0.y == e0.y) return line_intersects_coord(s1, e1, s0);
+    int c11 = orient_sign(s0, e0, s1);
+    int c12 = orient_sign(s0, e0, e1);
+    if (c11 != c12) {
+        int c21 = orient_sign(s1, e1, s0);
+        int c22 = orient_sign(s1, e1, e0);
+        return c21 != c22;
+    } else if (c11 == 0) {
+        return point_in_rect(s1, s0, e0) || point_in_rect(e1, s0, e0) || point_in_rect(e0, s1, e1);
+    }
+    return false;
+}
+
+// LineString x LineString intersects, warp cooperative.  Result is warp-uniform.
+__device__ __forceinline__ bool ls_intersects_ls(Coords A, int64_t na, Coords B, int64_t nb, int lane) {
+    if (na < 2 || nb < 2) return false;  // no lines() on either side
+    // has_disjoint_bboxes
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double ax0 = inf, ay0 = inf, ax1 = -inf, ay1 = -inf, bx0 = inf, by0 = inf, bx1 = -inf, by1 = -inf;
+    for (int64_t i = lane; i < na; i += 32) {
+        double2 q = A[i];
+        ax0 = fmin(ax0, q.x), ay0 = fmin(ay0, q.y), ax1 = fmax(ax1, q.x), ay1 = fmax(ay1, q.y);
+    }
+    for (int64_t i = lane; i < nb; i += 32) {
+        double2 q = B[i];
+        bx0 = fmin(bx0, q.x), by0 = fmin(by0, q.y), bx1 = fmax(bx1, q.x), by1 = fmax(by1, q.y);
+    }
+    ax0 = warp_min(ax0), ay0 = warp_min(ay0), ax1 = warp_max(ax1), ay1 = warp_max(ay1);
+    bx0 = warp_min(bx0), by0 = warp_min(by0), bx1 = warp_max(bx1), by1 = warp_max(by1);
+    if (ax0 > bx1 || bx0 > ax1 || ay0 > by1 || by0 > ay1) return false;
+    const int64_t sa = na - 1, sb = nb - 1, total = sa * sb;
+    for (int64_t base = 0; base < total; base += 32) {
+        int64_t t = base + lane;
+        bool hit = false;
+        if (t < total) {
+            int64_t i = t / sb, j = t - i * sb;
+            double2 a0 = A[i], a1 = A[i + 1], b0 = B[j], b1 = B[j + 1];
+            if (!seg_bbox_disjoint(a0, a1, b0, b1)) hit = line_intersects_line(b0, b1, a0, a1);
+        }
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    return false;
+}
+
+// squared distance point -> segment with the reference's case split and cross-product expression
+__device__ __forceinline__ double seg_dist2(double2 p, double2 s, double2 e) {
+    double dx = e.x - s.x, dy = e.y - s.y;
+    double wx = p.x - s.x, wy = p.y - s.y;
+    if (dx == 0.0 && dy == 0.0) return wx * wx + wy * wy;  // start == end
+    double dd = dx * dx + dy * dy;
+    double num = wx * dx + wy * dy;
+    if (num <= 0.0) return wx * wx + wy * wy;  // r <= 0
+    if (num >= dd) {                             // r >= 1 (exact: the correctly rounded quotient is >= 1 iff num >= dd)
+        double ux = p.x - e.x, uy = p.y - e.y;
+        return ux * ux + uy * uy;
+    }
+    double cross = (s.y - p.y) * dx - (s.x - p.x) * dy;
+    return (cross * cross) / dd;
+}
+
+__device__ __forceinline__ double ls_ls_min_dist2(Coords A, int64_t na, Coords B, int64_t nb, int lane) {
+    const double big = 1.7976931348623157e308;
+    double best = big;
+    const int64_t sa = na - 1, sb = nb - 1;
+    const int64_t t1 = nb * sa, total = t1 + na * sb;
+    for (int64_t t = lane; t < total; t += 32) {
+        double d;
+        if (t < t1) {  // vertex j of B against segment i of A
+            int64_t j = t / sa, i = t - j * sa;
+            d = seg_dist2(B[j], A[i], A[i + 1]);
+        } else {
+            int64_t u = t - t1;
+            int64_t i = u / sb, j = u - i * sb;
+            d = seg_dist2(A[i], B[j], B[j + 1]);
+        }
+        best = fmin(best, d);
+    }
+    return warp_min(best);
+}
+
+// stage a row's coordinates in shared memory when they fit, else hand back the global pointer
+__device__ __forceinline__ Coords stage(const double2 *__restrict__ g, int64_t c0, int64_t n, double2 *smem, bool fits, int lane) {
+    if (!fits) return Coords{g + c0};
+    for (int64_t i = lane; i < n; i += 32) smem[i] = __ldcs(g + c0 + i);
+    return Coords{smem};
+}
+
+// MODE 0: intersects -> byte per row   MODE 1: distance -> f64 (+ validity byte)
+template <int MODE>
+__global__ void __launch_bounds__(kPairWarps * 32) k_ls_ls(int64_t n, const double2 *__restrict__ axy,
+                                                           const int64_t *__restrict__ aoff, const uint8_t *__restrict__ avalid,
+                                                           const double2 *__restrict__ bxy, const int64_t *__restrict__ boff,
+                                                           const uint8_t *__restrict__ bvalid, uint8_t *__restrict__ out_bool,
+                                                           double *__restrict__ out_dist, uint8_t *__restrict__ out_valid) {
+    __shared__ double2 smem[kPairWarps][kPairSmemCoords];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * kPairWarps + wid;
+    const int64_t nwarps = (int64_t)gridDim.x * kPairWarps;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool valid = bit_get(avalid, r) && bit_get(bvalid, r);
+        int64_t a0 = aoff[r], na = aoff[r + 1] - a0, b0 = boff[r], nb = boff[r + 1] - b0;
+        bool fits = na + nb <= kPairSmemCoords;
+        __syncwarp();
+        Coords A = stage(axy, a0, na, smem[wid], fits, lane);
+        Coords B = stage(bxy, b0, nb, smem[wid] + (fits ? na : 0), fits, lane);
+        __syncwarp();
+        bool isect = valid && ls_intersects_ls(A, na, B, nb, lane);
+        if (MODE == 0) {
+            if (lane == 0) out_bool[r] = isect ? 1 : 0;
+        } else {
+            double d = 0.0;
+            bool ok = valid;
+            if (valid && !isect) {
+                if (na < 2 || nb < 2) {
+                    ok = false;  // reference: nearest_neighbor(..).unwrap() on an empty r-tree panics -> null
+                } else {
+                    d = sqrt(ls_ls_min_dist2(A, na, B, nb, lane));
+                }
+            }
+            if (lane == 0) {
+                out_dist[r] = ok ? d : nan("");
+                if (out_valid) out_valid[r] = ok ? 1 : 0;
+            }
+        }
+    }
+}
+
+// ---- point vs linestring / polygon -------------------------------------------------------------
+__device__ __forceinline__ double pt_dist(double2 a, double2 b) { return hypot(b.x - a.x, b.y - a.y); }
+// geo-types line_segment_distance (exact restatement, used where a row has few items)
+__device__ __forceinline__ double line_segment_distance(double2 p, double2 s, double2 e) {
+    if (s.x == e.x && s.y == e.y) return pt_dist(p, s);
+    double dx = e.x - s.x, dy = e.y - s.y;
+    double d2 = dx * dx + dy * dy;
+    double r = ((p.x - s.x) * dx + (p.y - s.y) * dy) / d2;
+    if (r <= 0.0) return pt_dist(p, s);
+    if (r >= 1.0) return pt_dist(p, e);
+    double sv = ((s.y - p.y) * dx - (s.x - p.x) * dy) / d2;
+    return fabs(sv) * hypot(dx, dy);
+}
+// geo-types line_string_contains_point (epsilon based, inexact by design), warp cooperative
+__device__ __forceinline__ bool line_string_contains_point(const double2 *__restrict__ xy, int64_t c0, int64_t n, double2 p,
+                                                           int lane) {
+    if (n == 0) return false;
+    if (n == 1) {
+        float d = (float)pt_dist(xy[c0], p);
+        return d <= 1.1920929e-07f;
+    }
+    bool hit = false;
+    for (int64_t i = lane; i < n; i += 32) {
+        double2 q = xy[c0 + i];
+        if (q.x == p.x && q.y == p.y) hit = true;
+    }
+    for (int64_t i = lane; i < n - 1; i += 32) {
+        double2 s = xy[c0 + i], e = xy[c0 + i + 1];
+        double dx = e.x - s.x, dy = e.y - s.y;
+        bool hx = dx != 0.0, hy = dy != 0.0;
+        double tx = hx ? (p.x - s.x) / dx : 0.0;
+        double ty = hy ? (p.y - s.y) / dy : 0.0;
+        bool c;
+        if (!hx && !hy) c = (p.x == s.x && p.y == s.y);
+        else if (hx && !hy) c = (p.y == s.y && 0.0 <= tx && tx <= 1.0);
+        else if (!hx && hy) c = (p.x == s.x && 0.0 <= ty && ty <= 1.0);
+        else c = (fabs(tx - ty) <= 2.220446049250313e-16 && 0.0 <= tx && tx <= 1.0);
+        hit = hit || c;
+    }
+    return __any_sync(0xffffffffu, hit);
+}
+__device__ __forceinline__ double point_ls_distance(const double2 *__restrict__ xy, int64_t c0, int64_t n, double2 p, int lane) {
+    if (n == 0 || line_string_contains_point(xy, c0, n, p, lane)) return 0.0;
+    double best = 1.7976931348623157e308;
+    for (int64_t i = lane; i < n - 1; i += 32) best = fmin(best, line_segment_distance(p, xy[c0 + i], xy[c0 + i + 1]));
+    return warp_min(best);
+}
+
+// coord_pos_relative_to_ring, warp cooperative: 0 outside, 1 boundary, 2 inside
+__device__ __forceinline__ int ring_position(const double2 *__restrict__ xy, int64_t c0, int64_t n, double2 p, int lane) {
+    if (n == 0) return 0;
+    if (n == 1) {
+        double2 q = xy[c0];
+        return (q.x == p.x && q.y == p.y) ? 1 : 0;
+    }
+    double2 first = xy[c0], last = xy[c0 + n - 1];
+    bool closing = !(first.x == last.x && first.y == last.y);  // Polygon::new would close the ring
+    int64_t nseg = n - 1 + (closing ? 1 : 0);
+    int wn = 0;
+    bool boundary = false;
+    for (int64_t i = lane; i < nseg; i += 32) {
+        double2 s = xy[c0 + i];
+        double2 e = (i + 1 < n) ? xy[c0 + i + 1] : first;
+        if (s.y <= p.y) {
+            if (e.y >= p.y) {
+                double o = orient2d(s.x, s.y, e.x, e.y, p.x, p.y);
+                if (o > 0.0 && e.y != p.y) wn += 1;
+                else if (o == 0.0 && value_in_between(p.x, s.x, e.x)) boundary = true;
+            }
+        } else if (e.y <= p.y) {
+            double o = orient2d(s.x, s.y, e.x, e.y, p.x, p.y);
+            if (o < 0.0) wn -= 1;
+            else if (o == 0.0 && value_in_between(p.x, s.x, e.x)) boundary = true;
+        }
+    }
+    if (__any_sync(0xffffffffu, boundary)) return 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    return wn == 0 ? 0 : 2;
+}
+// Polygon::calculate_coordinate_position over rings [r0,r1)
+__device__ __forceinline__ void polygon_position(const double2 *__restrict__ xy, const int64_t *__restrict__ ring_off, int64_t r0,
+                                                 int64_t r1, double2 p, int lane, bool &inside, int &boundary_count) {
+    if (r1 <= r0) return;
+    if (ring_off[r0 + 1] - ring_off[r0] == 0) return;
+    int pos = ring_position(xy, ring_off[r0], ring_off[r0 + 1] - ring_off[r0], p, lane);
+    if (pos == 0) return;
+    if (pos == 1) {
+        boundary_count += 1;
+        return;
+    }
+    for (int64_t r = r0 + 1; r < r1; ++r) {
+        int hp = ring_position(xy, ring_off[r], ring_off[r + 1] - ring_off[r], p, lane);
+        if (hp == 1) {
+            boundary_count += 1;
+            return;
+        }
+        if (hp == 2) return;
+    }
+    inside = true;
+}
+
+// poly rows vs point rows.  MODE 0: contains byte   MODE 1: distance
+template <int MODE>
+__global__ void __launch_bounds__(256) k_poly_point(int ptype, int64_t n, const double2 *__restrict__ pxy,
+                                                    const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
+                                                    const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ pvalid,
+                                                    const double2 *__restrict__ pts, const uint8_t *__restrict__ tvalid,
+                                                    uint8_t *__restrict__ out_bool, double *__restrict__ out_dist,
+                                                    uint8_t *__restrict__ out_valid) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool valid = bit_get(pvalid, r) && bit_get(tvalid, r);
+        double2 p = pts[r];
+        if (MODE == 0) {
+            bool res = false;
+            if (valid) {
+                if (ptype == GPL_POLYGON) {
+                    bool inside = false;
+                    int bc = 0;
+                    polygon_position(pxy, ring_off, geom_off[r], geom_off[r + 1], p, lane, inside, bc);
+                    res = (bc % 2 == 0) && inside;
+                } else {
+                    for (int64_t q = geom_off[r]; q < geom_off[r + 1] && !res; ++q) {
+                        bool inside = false;
+                        int bc = 0;
+                        polygon_position(pxy, ring_off, part_off[q], part_off[q + 1], p, lane, inside, bc);
+                        res = (bc % 2 == 0) && inside;
+                    }
+                }
+            }
+            if (lane == 0) out_bool[r] = res ? 1 : 0;
+        } else {  // Point-Polygon distance (POLYGON rows only)
+            double d = nan("");
+            if (valid) {
+                int64_t r0 = geom_off[r], r1 = geom_off[r + 1];
+                if (r1 <= r0 || ring_off[r0 + 1] - ring_off[r0] == 0) {
+                    d = 0.0;
+                } else {
+                    bool inside = false;
+                    int bc = 0;
+                    polygon_position(pxy, ring_off, r0, r1, p, lane, inside, bc);
+                    if (bc % 2 == 1 || inside) {
+                        d = 0.0;
+                    } else {
+                        double acc = 1.7976931348623157e308;
+                        for (int64_t h = r0 + 1; h < r1; ++h)
+                            acc = fmin(acc, point_ls_distance(pxy, ring_off[h], ring_off[h + 1] - ring_off[h], p, lane));
+                        double ext = 1.7976931348623157e308;
+                        int64_t c0 = ring_off[r0], nn = ring_off[r0 + 1] - c0;
+                        for (int64_t i = lane; i < nn - 1; i += 32) ext = fmin(ext, line_segment_distance(p, pxy[c0 + i], pxy[c0 + i + 1]));
+                        d = fmin(acc, warp_min(ext));
+                    }
+                }
+            }
+            if (lane == 0) {
+                out_dist[r] = d;
+                if (out_valid) out_valid[r] = valid ? 1 : 0;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_point_ls_dist(int64_t n, const double2 *__restrict__ pts, const uint8_t *__restrict__ tvalid,
+                                                       const double2 *__restrict__ lxy, const int64_t *__restrict__ loff,
+                                                       const uint8_t *__restrict__ lvalid, double *__restrict__ out,
+                                                       uint8_t *__restrict__ out_valid) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool valid = bit_get(tvalid, r) && bit_get(lvalid, r);
+        double d = nan("");
+        if (valid) d = point_ls_distance(lxy, loff[r], loff[r + 1] - loff[r], pts[r], lane);
+        if (lane == 0) {
+            out[r] = d;
+            if (out_valid) out_valid[r] = valid ? 1 : 0;
+        }
+    }
+}
+__global__ void k_point_point_dist(int64_t n, const double2 *__restrict__ a, const uint8_t *__restrict__ av,
+                                   const double2 *__restrict__ b, const uint8_t *__restrict__ bv, double *__restrict__ out,
+                                   uint8_t *__restrict__ out_valid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool valid = bit_get(av, i) && bit_get(bv, i);
+    out[i] = valid ? pt_dist(a[i], b[i]) : nan("");
+    if (out_valid) out_valid[i] = valid ? 1 : 0;
+}
+
+int pack_bits(gpl_ctx *ctx, const uint8_t *bytes_dev, uint8_t *bitmap_dev, int64_t n);
+int deliver(gpl_ctx *ctx, void *dst, const void *src_dev, size_t bytes, int mem);
+
+static int warp_grid(int64_t rows, int warps_per_cta) {
+    int64_t want = ceil_div(rows, warps_per_cta);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * 16));
+}
+
+static const char *type_name(int t) {
+    switch (t) {
+    case GPL_POINT: return "Point";
+    case GPL_LINESTRING: return "LineString";
+    case GPL_POLYGON: return "Polygon";
+    case GPL_MULTIPOINT: return "MultiPoint";
+    case GPL_MULTILINESTRING: return "MultiLineString";
+    case GPL_MULTIPOLYGON: return "MultiPolygon";
+    default: return "Unknown";
+    }
+}
+
+// bool result: bytes on device -> Arrow bitmap in the caller's memory
+static int finish_bitmap(gpl_ctx *ctx, const uint8_t *bytes_dev, int64_t n, uint8_t *out_bitmap, int mem) {
+    size_t nb = (size_t)(n + 7) / 8;
+    if (mem == GPL_DEVICE) return pack_bits(ctx, bytes_dev, out_bitmap, n);
+    Scratch<uint8_t> bm;
+    GPL_TRY(bm.get(ctx, nb));
+    GPL_TRY(pack_bits(ctx, bytes_dev, bm.p, n));
+    return deliver(ctx, out_bitmap, bm.p, nb, GPL_HOST);
+}
+
+}  // namespace gpl
+
+using namespace gpl;
+
+extern "C" int gpl_intersects(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, uint8_t *out_bitmap, int mem) {
+    GPL_REQUIRE(ctx && a && b && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_intersects: NULL argument");
+    GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "intersects: lengths differ (%lld vs %lld)",
+                (long long)a->n_geoms, (long long)b->n_geoms);
+    GPL_REQUIRE(a->type == GPL_LINESTRING && b->type == GPL_LINESTRING, GPL_ERR_INVALID_TYPE,
+                "Expected LineString x LineString (found %s x %s)", type_name(a->type), type_name(b->type));
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    int64_t n = a->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<uint8_t> bytes;
+    GPL_TRY(bytes.get(ctx, (size_t)n));
+    GPL_LAUNCH(ctx, k_ls_ls<0>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, reinterpret_cast<const double2 *>(a->xy),
+               a->geom_off, a->validity, reinterpret_cast<const double2 *>(b->xy), b->geom_off, b->validity, bytes.p, nullptr,
+               nullptr);
+    return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
+}
+
+extern "C" int gpl_contains(gpl_ctx *ctx, const gpl_array *polygons, const gpl_array *points, uint8_t *out_bitmap, int mem) {
+    GPL_REQUIRE(ctx && polygons && points && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_contains: NULL argument");
+    GPL_REQUIRE(polygons->n_geoms == points->n_geoms, GPL_ERR_LENGTH_MISMATCH, "contains: lengths differ (%lld vs %lld)",
+                (long long)polygons->n_geoms, (long long)points->n_geoms);
+    GPL_REQUIRE((polygons->type == GPL_POLYGON || polygons->type == GPL_MULTIPOLYGON) && points->type == GPL_POINT,
+                GPL_ERR_INVALID_TYPE, "Expected (Multi)Polygon x Point (found %s x %s)", type_name(polygons->type),
+                type_name(points->type));
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    int64_t n = polygons->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<uint8_t> bytes;
+    GPL_TRY(bytes.get(ctx, (size_t)n));
+    GPL_LAUNCH(ctx, k_poly_point<0>, warp_grid(n, 8), 256, 0, polygons->type, n, reinterpret_cast<const double2 *>(polygons->xy),
+               polygons->geom_off, polygons->part_off, polygons->ring_off, polygons->validity,
+               reinterpret_cast<const double2 *>(points->xy), points->validity, bytes.p, nullptr, nullptr);
+    return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
+}
+
+extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, double *out, uint8_t *out_validity, int mem) {
+    GPL_REQUIRE(ctx && a && b && out, GPL_ERR_INVALID_ARG, "gpl_distance: NULL argument");
+    GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "distance: lengths differ (%lld vs %lld)",
+                (long long)a->n_geoms, (long long)b->n_geoms);
+    const int ta = a->type, tb = b->type;
+    bool ok = (ta == GPL_POINT && (tb == GPL_POINT || tb == GPL_LINESTRING || tb == GPL_POLYGON)) ||
+              (ta == GPL_LINESTRING && (tb == GPL_POINT || tb == GPL_LINESTRING)) || (ta == GPL_POLYGON && tb == GPL_POINT);
+    GPL_REQUIRE(ok, GPL_ERR_INVALID_TYPE, "distance: unsupported geometry pair %s x %s", type_name(ta), type_name(tb));
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    int64_t n = a->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<double> tmp;
+    Scratch<uint8_t> vbytes;
+    double *dst = out;
+    if (mem == GPL_HOST) {
+        GPL_TRY(tmp.get(ctx, (size_t)n));
+        dst = tmp.p;
+    }
+    uint8_t *vb = nullptr;
+    if (out_validity) {
+        GPL_TRY(vbytes.get(ctx, (size_t)n));
+        vb = vbytes.p;
+    }
+    const double2 *axy = reinterpret_cast<const double2 *>(a->xy), *bxy = reinterpret_cast<const double2 *>(b->xy);
+    if (ta == GPL_LINESTRING && tb == GPL_LINESTRING) {
+        GPL_LAUNCH(ctx, k_ls_ls<1>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,
+                   b->validity, nullptr, dst, vb);
+    } else if (ta == GPL_POINT && tb == GPL_POINT) {
+        GPL_LAUNCH(ctx, k_point_point_dist, (int)ceil_div(n, 256), 256, 0, n, axy, a->validity, bxy, b->validity, dst, vb);
+    } else if (ta == GPL_POINT && tb == GPL_LINESTRING) {
+        GPL_LAUNCH(ctx, k_point_ls_dist, warp_grid(n, 8), 256, 0, n, axy, a->validity, bxy, b->geom_off, b->validity, dst, vb);
+    } else if (ta == GPL_LINESTRING && tb == GPL_POINT) {
+        GPL_LAUNCH(ctx, k_point_ls_dist, warp_grid(n, 8), 256, 0, n, bxy, b->validity, axy, a->geom_off, a->validity, dst, vb);
+    } else if (ta == GPL_POINT && tb == GPL_POLYGON) {
+        GPL_LAUNCH(ctx, k_poly_point<1>, warp_grid(n, 8), 256, 0, b->type, n, bxy, b->geom_off, b->part_off, b->ring_off, b->validity,
+                   axy, a->validity, nullptr, dst, vb);
+    } else {
+        GPL_LAUNCH(ctx, k_poly_point<1>, warp_grid(n, 8), 256, 0, a->type, n, axy, a->geom_off, a->part_off, a->ring_off, a->validity,
+                   bxy, b->validity, nullptr, dst, vb);
+    }
+    if (out_validity) GPL_TRY(finish_bitmap(ctx, vb, n, out_validity, mem));
+    return deliver(ctx, out, dst, sizeof(double) * n, mem);
+}

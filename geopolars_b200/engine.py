@@ -1,0 +1,394 @@
+"""Thin object layer over the C ABI: Context (device + stream), DeviceArray (GeoArrow in HBM),
+PipIndex (polygon side of a contains join) and one function per GeoSeries op.
+
+Reference boundary mirrored: `impl GeoSeries for Series` (geopolars/geopolars-geo/src/geoseries.rs:10-181)
+— same op names and argument meaning; errors map to the reference's exception classes
+(py-geopolars/src/error.rs:27-60).  Everything here calls libgeopolars_b200.so; nothing falls back
+to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import GPL_DEVICE, GPL_HOST, check
+from .geoarrow import GeoArrowArray, GeometryType
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One per (host thread, device).  `stream` is a raw cudaStream_t (int) to enqueue on, e.g.
+    torch.cuda.current_stream().cuda_stream, or None for a private non-blocking stream."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = device
+        h = C.c_void_p()
+        check(self.lib.gpl_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+
+    def set_stream(self, stream: Optional[int]) -> None:
+        check(self.lib.gpl_ctx_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    def synchronize(self) -> None:
+        check(self.lib.gpl_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.gpl_ctx_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gpl_ctx_destroy(self._h)
+            self._h = None
+
+    # -- arrays ------------------------------------------------------------------------------------
+    def upload(self, arr: GeoArrowArray, offset_width: int = 64) -> "DeviceArray":
+        """Copy a host GeoArrow array to HBM once (cudaMemcpyAsync on the context stream)."""
+        b = _lib.Buffers()
+        keep = []
+        b.geom_type = int(arr.type)
+        b.offset_width = offset_width
+        b.mem = GPL_HOST
+        b.n_geoms, b.n_parts, b.n_rings, b.n_coords = len(arr), arr.n_parts, arr.n_rings, arr.n_coords
+        b.x = arr.xy.ctypes.data
+        b.y = None
+        dt = np.int64 if offset_width == 64 else np.int32
+        for name, field in (("geom_off", "geom_offsets"), ("part_off", "part_offsets"), ("ring_off", "ring_offsets")):
+            v = getattr(arr, name)
+            if v is not None:
+                vv = np.ascontiguousarray(v, dtype=dt)
+                keep.append(vv)
+                setattr(b, field, vv.ctypes.data)
+        bm = arr.validity_bitmap()
+        if bm is not None:
+            keep.append(bm)
+            b.validity = bm.ctypes.data
+        h = C.c_void_p()
+        check(self.lib.gpl_array_from_buffers(self._h, C.byref(b), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def upload_separated(self, type: GeometryType, x: np.ndarray, y: np.ndarray, geom_off=None, part_off=None, ring_off=None,
+                         valid=None, offset_width: int = 32) -> "DeviceArray":
+        """GeoArrow Struct{x,y} coordinates (what py-geopolars builds, internals/geoseries.py:87-107)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        b = _lib.Buffers()
+        keep = [x, y]
+        b.geom_type = int(type)
+        b.offset_width = offset_width
+        b.mem = GPL_HOST
+        b.n_coords = x.shape[0]
+        dt = np.int64 if offset_width == 64 else np.int32
+        offs = {"geom_offsets": geom_off, "part_offsets": part_off, "ring_offsets": ring_off}
+        for field, v in offs.items():
+            if v is not None:
+                vv = np.ascontiguousarray(v, dtype=dt)
+                keep.append(vv)
+                setattr(b, field, vv.ctypes.data)
+        b.n_geoms = x.shape[0] if int(type) == GeometryType.POINT else len(geom_off) - 1
+        b.n_parts = 0 if part_off is None else len(part_off) - 1
+        b.n_rings = 0 if ring_off is None else len(ring_off) - 1
+        b.x, b.y = x.ctypes.data, y.ctypes.data
+        if valid is not None:
+            bm = np.packbits(np.asarray(valid, dtype=bool), bitorder="little")
+            keep.append(bm)
+            b.validity = bm.ctypes.data
+        h = C.c_void_p()
+        check(self.lib.gpl_array_from_buffers(self._h, C.byref(b), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def wrap_device(self, type: GeometryType, n_geoms: int, n_coords: int, xy_ptr: int, geom_off_ptr: int = 0,
+                    part_off_ptr: int = 0, ring_off_ptr: int = 0, n_parts: int = 0, n_rings: int = 0, validity_ptr: int = 0,
+                    keepalive=None) -> "DeviceArray":
+        """Borrow buffers that already live in HBM (interleaved xy, int64 offsets): zero copies."""
+        b = _lib.Buffers()
+        b.geom_type = int(type)
+        b.offset_width = 64
+        b.mem = GPL_DEVICE
+        b.n_geoms, b.n_parts, b.n_rings, b.n_coords = n_geoms, n_parts, n_rings, n_coords
+        b.x = xy_ptr
+        b.y = None
+        b.geom_offsets = geom_off_ptr or None
+        b.part_offsets = part_off_ptr or None
+        b.ring_offsets = ring_off_ptr or None
+        b.validity = validity_ptr or None
+        h = C.c_void_p()
+        check(self.lib.gpl_array_from_buffers(self._h, C.byref(b), C.byref(h)))
+        d = DeviceArray(self, h)
+        d._keepalive = keepalive
+        return d
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """A GeoArrow geometry array resident in HBM (opaque gpl_array handle)."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._h = handle
+        self._keepalive = None
+
+    def view(self) -> _lib.DeviceView:
+        v = _lib.DeviceView()
+        check(self.ctx.lib.gpl_array_view(self._h, C.byref(v)))
+        return v
+
+    @property
+    def type(self) -> GeometryType:
+        return GeometryType(self.view().geom_type)
+
+    def __len__(self) -> int:
+        return int(self.view().n_geoms)
+
+    def to_host(self) -> GeoArrowArray:
+        v = self.view()
+        t = GeometryType(v.geom_type)
+        xy = np.empty((v.n_coords, 2), dtype=np.float64)
+        geom = np.empty(v.n_geoms + 1, dtype=np.int64) if v.geom_offsets else None
+        part = np.empty(v.n_parts + 1, dtype=np.int64) if v.part_offsets else None
+        ring = np.empty(v.n_rings + 1, dtype=np.int64) if v.ring_offsets else None
+        bm = np.empty((v.n_geoms + 7) // 8, dtype=np.uint8) if v.validity else None
+        check(self.ctx.lib.gpl_array_copy_out(self.ctx._h, self._h, _np_ptr(xy), _np_ptr(geom), _np_ptr(part), _np_ptr(ring),
+                                              _np_ptr(bm), GPL_HOST))
+        valid = None
+        if bm is not None:
+            valid = np.unpackbits(bm, bitorder="little")[: v.n_geoms].astype(bool)
+            if valid.all():
+                valid = None
+        return GeoArrowArray(t, xy, geom_off=geom, part_off=part, ring_off=ring, valid=valid)
+
+    def free(self) -> None:
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx.lib.gpl_array_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _out_array(ctx: Context, fn, *args) -> DeviceArray:
+    h = C.c_void_p()
+    check(fn(ctx._h, *args, C.byref(h)))
+    return DeviceArray(ctx, h)
+
+
+def _bits(bm: np.ndarray, n: int) -> np.ndarray:
+    return np.unpackbits(bm, bitorder="little")[:n].astype(bool)
+
+
+# ---- GeoSeries ops (names follow geoseries.rs:10-181) -------------------------------------------
+def affine_transform(a: DeviceArray, m: Sequence[float]) -> DeviceArray:
+    """m = (a, b, xoff, d, e, yoff): x' = a*x + b*y + xoff ; y' = d*x + e*y + yoff."""
+    aa, b, xoff, d, e, yoff = [float(v) for v in m]
+    return _out_array(a.ctx, a.ctx.lib.gpl_affine_transform, a._h, aa, b, xoff, d, e, yoff)
+
+
+def translate(a: DeviceArray, xoff: float = 0.0, yoff: float = 0.0) -> DeviceArray:
+    return _out_array(a.ctx, a.ctx.lib.gpl_translate, a._h, float(xoff), float(yoff))
+
+
+def _origin(origin) -> Tuple[int, float, float]:
+    """TransformOrigin parsing, same rules as py-geopolars/src/utils.rs:5-27."""
+    if isinstance(origin, str):
+        s = origin.lower()
+        if s == "centroid":
+            return _lib.ORIGIN_CENTROID, 0.0, 0.0
+        if s == "center":
+            return _lib.ORIGIN_CENTER, 0.0, 0.0
+        raise ValueError("Invalid argument")
+    if isinstance(origin, dict):
+        return _lib.ORIGIN_POINT, float(origin["x"]), float(origin["y"])
+    x, y = origin
+    return _lib.ORIGIN_POINT, float(x), float(y)
+
+
+def scale(a: DeviceArray, xfact: float = 1.0, yfact: float = 1.0, origin="center") -> DeviceArray:
+    k, ox, oy = _origin(origin)
+    return _out_array(a.ctx, a.ctx.lib.gpl_scale, a._h, float(xfact), float(yfact), k, ox, oy)
+
+
+def rotate(a: DeviceArray, angle: float, origin="center") -> DeviceArray:
+    k, ox, oy = _origin(origin)
+    return _out_array(a.ctx, a.ctx.lib.gpl_rotate, a._h, float(angle), k, ox, oy)
+
+
+def skew(a: DeviceArray, xs: float = 0.0, ys: float = 0.0, origin="center") -> DeviceArray:
+    k, ox, oy = _origin(origin)
+    return _out_array(a.ctx, a.ctx.lib.gpl_skew, a._h, float(xs), float(ys), k, ox, oy)
+
+
+def area(a: DeviceArray) -> np.ndarray:
+    out = np.empty(len(a), dtype=np.float64)
+    check(a.ctx.lib.gpl_area(a.ctx._h, a._h, _np_ptr(out), GPL_HOST))
+    return out
+
+
+def euclidean_length(a: DeviceArray) -> np.ndarray:
+    out = np.empty(len(a), dtype=np.float64)
+    check(a.ctx.lib.gpl_euclidean_length(a.ctx._h, a._h, _np_ptr(out), GPL_HOST))
+    return out
+
+
+def centroid(a: DeviceArray) -> DeviceArray:
+    return _out_array(a.ctx, a.ctx.lib.gpl_centroid, a._h)
+
+
+def envelope(a: DeviceArray) -> DeviceArray:
+    h = C.c_void_p()
+    check(a.ctx.lib.gpl_envelope(a.ctx._h, a._h, C.byref(h), None, GPL_HOST))
+    return DeviceArray(a.ctx, h)
+
+
+def bounds(a: DeviceArray) -> np.ndarray:
+    """minx, miny, maxx, maxy per geometry (NaN for empty)."""
+    out = np.empty((len(a), 4), dtype=np.float64)
+    check(a.ctx.lib.gpl_envelope(a.ctx._h, a._h, None, _np_ptr(out), GPL_HOST))
+    return out
+
+
+def convex_hull(a: DeviceArray) -> DeviceArray:
+    return _out_array(a.ctx, a.ctx.lib.gpl_convex_hull, a._h)
+
+
+def exterior(a: DeviceArray) -> DeviceArray:
+    return _out_array(a.ctx, a.ctx.lib.gpl_exterior, a._h)
+
+
+def explode(a: DeviceArray) -> DeviceArray:
+    return _out_array(a.ctx, a.ctx.lib.gpl_explode, a._h)
+
+
+def distance(a: DeviceArray, b: DeviceArray) -> Tuple[np.ndarray, np.ndarray]:
+    n = len(a)
+    out = np.empty(n, dtype=np.float64)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(a.ctx.lib.gpl_distance(a.ctx._h, a._h, b._h, _np_ptr(out), _np_ptr(bm), GPL_HOST))
+    return out, _bits(bm, n)
+
+
+def intersects(a: DeviceArray, b: DeviceArray) -> np.ndarray:
+    n = len(a)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(a.ctx.lib.gpl_intersects(a.ctx._h, a._h, b._h, _np_ptr(bm), GPL_HOST))
+    return _bits(bm, n)
+
+
+def contains(polygons: DeviceArray, points: DeviceArray) -> np.ndarray:
+    n = len(polygons)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(polygons.ctx.lib.gpl_contains(polygons.ctx._h, polygons._h, points._h, _np_ptr(bm), GPL_HOST))
+    return _bits(bm, n)
+
+
+def geom_type(a: DeviceArray) -> np.ndarray:
+    out = np.empty(len(a), dtype=np.int8)
+    check(a.ctx.lib.gpl_geom_type(a.ctx._h, a._h, _np_ptr(out), GPL_HOST))
+    return out
+
+
+def is_empty(a: DeviceArray) -> np.ndarray:
+    n = len(a)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(a.ctx.lib.gpl_is_empty(a.ctx._h, a._h, _np_ptr(bm), GPL_HOST))
+    return _bits(bm, n)
+
+
+def is_ring(a: DeviceArray) -> np.ndarray:
+    n = len(a)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(a.ctx.lib.gpl_is_ring(a.ctx._h, a._h, _np_ptr(bm), GPL_HOST))
+    return _bits(bm, n)
+
+
+def x(a: DeviceArray) -> np.ndarray:
+    out = np.empty(len(a), dtype=np.float64)
+    check(a.ctx.lib.gpl_x(a.ctx._h, a._h, _np_ptr(out), GPL_HOST))
+    return out
+
+
+def y(a: DeviceArray) -> np.ndarray:
+    out = np.empty(len(a), dtype=np.float64)
+    check(a.ctx.lib.gpl_y(a.ctx._h, a._h, _np_ptr(out), GPL_HOST))
+    return out
+
+
+# ---- spatial join -------------------------------------------------------------------------------
+class PipIndex:
+    """Polygon side of a points-in-polygons join; stands in for SpatialIndex
+    (geopolars/src/spatial_index.rs:314-350)."""
+
+    def __init__(self, polygons: DeviceArray):
+        self.ctx = polygons.ctx
+        self.polygons = polygons  # keep alive: the index references its coordinates
+        h = C.c_void_p()
+        check(self.ctx.lib.gpl_pip_index_build(self.ctx._h, polygons._h, C.byref(h)))
+        self._h = h
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.ctx.lib.gpl_pip_index_bytes(self._h))
+
+    def query(self, points_xy: np.ndarray, with_count: bool = False):
+        """first containing polygon row per point (-1 = none) [+ number of containing rows]."""
+        pts = np.ascontiguousarray(points_xy, dtype=np.float64).reshape(-1, 2)
+        n = pts.shape[0]
+        first = np.empty(n, dtype=np.int32)
+        cnt = np.empty(n, dtype=np.int32) if with_count else None
+        check(self.ctx.lib.gpl_contains_join(self.ctx._h, self._h, _np_ptr(pts), n, _np_ptr(first), _np_ptr(cnt), GPL_HOST))
+        return (first, cnt) if with_count else first
+
+    def query_device(self, points_ptr: int, n: int, first_ptr: int, count_ptr: int = 0) -> None:
+        """all buffers already in HBM (bench `value` path): one kernel launch, stream ordered."""
+        check(self.ctx.lib.gpl_contains_join(self.ctx._h, self._h, C.c_void_p(points_ptr), n, C.c_void_p(first_ptr),
+                                             C.c_void_p(count_ptr) if count_ptr else None, GPL_DEVICE))
+
+    def query_array(self, points: DeviceArray, with_count: bool = False):
+        n = len(points)
+        first = np.empty(n, dtype=np.int32)
+        cnt = np.empty(n, dtype=np.int32) if with_count else None
+        check(self.ctx.lib.gpl_contains_join_array(self.ctx._h, self._h, points._h, _np_ptr(first), _np_ptr(cnt), GPL_HOST))
+        return (first, cnt) if with_count else first
+
+    def query_host_pipelined(self, points_ptr: int, n: int, first_ptr: int, chunk_points: int = 0) -> None:
+        """host (ideally pinned) buffers; H2D / kernel / D2H overlapped in chunks (bench `e2e` path)."""
+        check(self.ctx.lib.gpl_contains_join_host(self.ctx._h, self._h, C.c_void_p(points_ptr), n, C.c_void_p(first_ptr),
+                                                  chunk_points))
+
+    def pairs(self, points_xy: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """(lhs point index, rhs polygon row) pairs, the reference's join output (spatial_index.rs:139-157)."""
+        pts = np.ascontiguousarray(points_xy, dtype=np.float64).reshape(-1, 2)
+        n = pts.shape[0]
+        total = C.c_int64(0)
+        check(self.ctx.lib.gpl_contains_join_pairs(self.ctx._h, self._h, _np_ptr(pts), n, None, None, C.byref(total), GPL_HOST))
+        lhs = np.empty(total.value, dtype=np.uint64)
+        rhs = np.empty(total.value, dtype=np.uint64)
+        if total.value:
+            check(self.ctx.lib.gpl_contains_join_pairs(self.ctx._h, self._h, _np_ptr(pts), n, _np_ptr(lhs), _np_ptr(rhs),
+                                                       C.byref(total), GPL_HOST))
+        return lhs, rhs
+
+    def free(self) -> None:
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx.lib.gpl_pip_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
