@@ -124,6 +124,12 @@ extern "C" int gpl_ctx_create(int device, void *stream, gpl_ctx **out) {
     GPL_CUDA(cudaSetDevice(device));
     gpl_ctx *c = new gpl_ctx();
     c->device = device;
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess) c->l2_persist_max = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess) c->l2_window_max = (size_t)v;
+        (void)cudaGetLastError();
+    }
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

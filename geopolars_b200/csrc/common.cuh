@@ -62,6 +62,8 @@ struct gpl_ctx {
     std::multimap<size_t, void *> free_blocks;  // size -> ptr
     std::map<void *, size_t> live;              // ptr -> size (blocks handed out)
     size_t bytes_reserved = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;  // device limits, read once at creation
+    const void *l2_pinned = nullptr;               // slab currently covered by the access-policy window
 
     int alloc(size_t bytes, void **out);
     void release(void *p);

@@ -10,12 +10,18 @@
 //   * output = (lhs_index, rhs_index) pairs (spatial_index.rs:139-157).
 //
 // B200 design.  The polygon side is small (10 MB) and lives in the 126 MB L2; the point side is a
-// 1.6 GB stream.  So the kernel is "one thread per point, streaming LDG.128 of the point, gathers
-// from an L2-resident index":
-//   grid cell (arithmetic)  -> candidate polygon parts (sorted, so the first hit is the lowest row)
-//   part header (64 B)      -> bbox reject, y-bucket parameters
-//   y-bucket (arithmetic)   -> short list of 32-byte edge records whose closed y-range can contain p.y
-//   exact winding test over that list only.
+// 1.6 GB stream.  Random points make every index access a gather, and a gather costs one L1 wavefront
+// per distinct 128-byte line per load instruction (measured: the first thread-per-point version of this
+// kernel sat at 84 % l1tex throughput).  The layout and the kernel are built around that limit:
+//   grid cell (arithmetic)  -> ONE 32-byte record = candidate count + the first candidate's x-range and
+//                              y-bucket parameters (one 256-bit load)
+//   y-bucket (arithmetic)   -> (start,end) of a short list of 32-byte edge records whose closed y-range
+//                              can contain p.y (one 64-bit load)
+//   edge records            -> the 32 lanes of a warp pool the edge lists of their 32 points and walk
+//                              the pooled list 32 records at a time (one 256-bit load per record,
+//                              neighbouring lanes read neighbouring records => ~3 edges per wavefront),
+//                              winding contributions go to the owning point through shared-memory
+//                              atomics.  No lane idles while another walks a long list.
 // Exactness of the pruning: geo's loop only ever acts on an edge when p.y lies in the edge's closed
 // y-range.  Buckets are assigned with f(y) = clamp(floor((y - ymin) * inv_h)), a monotone
 // non-decreasing function of y in IEEE arithmetic (subtraction, multiplication by a positive constant,
@@ -24,22 +30,55 @@
 // the reference would act on, and every listed edge is evaluated with the reference's own rule.
 // The same argument covers the grid cells (bbox filter).  No epsilon anywhere.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "scan.cuh"
 
+
 namespace gpl {
 
-struct __align__(16) PartHeader {  // 64 bytes, two L2 sectors
+struct __align__(16) PartHeader {  // build-time record (double-precision bbox), 64 bytes
     double xmin, ymin, xmax, ymax;
-    double inv_h;          // n_buckets / (ymax - ymin), 0 when degenerate
+    double inv_h;          // (double)(float)(n_buckets / (ymax - by0)), 0 when degenerate
     int32_t n_buckets;
     int32_t bucket_base;   // first bucket of this part in bucket_start[]
     int32_t geom;          // parent row in the polygon array
     int32_t flags;         // bit0: has holes (entries carry ring ids), bit1: valid
-    double pad;
+    double by0;            // bucket origin: (double)float_round_down(ymin)
 };
 static_assert(sizeof(PartHeader) == 64, "PartHeader must be 64 bytes");
+
+// Query-time part parameters (24 bytes).  All FLOAT, all CONSERVATIVE:
+//   xminf/xmaxf  the x-range rounded outwards: can only fail to reject, never reject a point inside;
+//   yminf        the bucket origin, ymin rounded DOWN;  inv_hf = n_buckets / (ymax - yminf).
+// The bucket function f(y) = min(floor((y - yminf) * inv_hf), nb-1) is evaluated in double on these
+// float-valued parameters, identically at build and query time, so it is the same monotone function
+// on both sides (that is all the exactness argument needs).  t < 0 <=> y < yminf <= ymin, and
+// t >= nb + 1 implies y > ymax (inv_hf carries a relative error of 2^-23, nb <= 4096).
+struct PartLite {
+    float xminf, xmaxf, yminf, inv_hf;
+    int32_t nb_flags;     // n_buckets in bits 0..23, bit 31: part has holes
+    int32_t bucket_base;
+};
+// one 32-byte sector per part: parameters + parent row (candidates after the first of a cell)
+struct __align__(32) PartRec {
+    PartLite lite;
+    int32_t geom;
+    int32_t pad;
+};
+static_assert(sizeof(PartRec) == 32, "PartRec must be one sector");
+
+// grid cell: one sector.  count == 1: `first` is the part id and `lite` its parameters — the common
+// case costs a single 256-bit load.  count > 1: `first` is the offset of the ascending part-id list in
+// cell_items[], `lite` belongs to the first (lowest) of them.
+struct __align__(32) CellRec {
+    int32_t count;
+    int32_t first;
+    PartLite lite;
+};
+static_assert(sizeof(CellRec) == 32, "CellRec must be one sector");
 
 struct __align__(32) EdgeRec {  // one L2 sector
     double sx, sy, ex, ey;
@@ -56,16 +95,20 @@ struct GridParams {
 struct gpl_pip_index {
     gpl_ctx *ctx = nullptr;
     const gpl_array *polys = nullptr;
-    int64_t n_parts = 0, n_geoms = 0, n_buckets = 0, n_entries = 0, n_cell_items = 0;
-    int32_t gx = 0, gy = 0;
-    gpl::PartHeader *parts = nullptr;
-    gpl::GridParams *grid = nullptr;  // device copy
-    int32_t *cell_start = nullptr;    // gx*gy + 1
-    int32_t *cell_items = nullptr;    // part ids, ascending per cell
-    int32_t *bucket_start = nullptr;  // n_buckets + 1
+    int64_t n_parts = 0, n_geoms = 0, n_buckets = 0, n_entries = 0, n_overflow = 0;
+    gpl::GridParams grid;            // host copy, passed to the query kernel by value
+    // one slab (so that a single L2 persisting access-policy window covers the whole index)
+    uint8_t *slab = nullptr;
+    size_t slab_bytes = 0;
+    gpl::PartRec *parts = nullptr;
+    gpl::CellRec *cells = nullptr;    // gx*gy
+    int32_t *cell_overflow = nullptr; // ascending part ids of the cells with more than one candidate
+    int2 *bucket_range = nullptr;     // n_buckets: (start, end) into entries[]
     gpl::EdgeRec *entries = nullptr;
-    int32_t *entry_ring = nullptr;  // ring index within part (0 = exterior), only if any part has holes
+    int32_t *entry_ring = nullptr;    // ring index within part (0 = exterior), only if any part has holes
+    bool multi = false;               // MULTIPOLYGON: parts[].geom differs from the part id
     bool any_holes = false;
+    unsigned long long *n_deferred = nullptr;  // device counter inside the slab
     int64_t bytes = 0;
 };
 
@@ -128,14 +171,17 @@ __global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts,
             int64_t nb = valid ? (n_slots + 1) / 2 : 0;
             if (nb < 1) nb = valid ? 1 : 0;
             if (nb > 4096) nb = 4096;
-            double h_ext = y1 - y0;
-            h.inv_h = (valid && h_ext > 0.0 && isfinite(h_ext)) ? (double)nb / h_ext : 0.0;
-            if (!isfinite(h.inv_h)) h.inv_h = 0.0;
+            float yminf = __double2float_rd(y0);
+            double by0 = (double)yminf;
+            double h_ext = y1 - by0;
+            float inv_hf = (valid && h_ext > 0.0 && isfinite(h_ext)) ? __double2float_rn((double)nb / h_ext) : 0.0f;
+            if (!isfinite(inv_hf)) inv_hf = 0.0f;
+            h.by0 = by0;
+            h.inv_h = (double)inv_hf;
             h.n_buckets = (int32_t)nb;
             h.bucket_base = 0;
             h.geom = g;
             h.flags = (valid ? 2 : 0) | ((r1 - r0 > 1) ? 1 : 0);
-            h.pad = 0.0;
             parts[p] = h;
             nb_out[p] = (int32_t)nb;
         }
@@ -182,10 +228,11 @@ __device__ __forceinline__ int32_t mono_index(double v, double lo, double inv, i
     return (int32_t)t;
 }
 
-// pass 0 counts, pass 1 fills: one thread per part walks the cells its bbox overlaps
+// pass 0 counts, pass 1 fills cell_items (segment per cell): one thread per part walks the cells its
+// bbox overlaps.
 template <int PASS>
 __global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, const GridParams *__restrict__ gp,
-                        int32_t *__restrict__ cell_count_or_cursor, int32_t *__restrict__ cell_items) {
+                        int32_t *__restrict__ count_or_cursor, int32_t *__restrict__ items) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartHeader h = parts[p];
@@ -197,12 +244,62 @@ __global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, c
         for (int32_t cx = cx0; cx <= cx1; ++cx) {
             int64_t c = (int64_t)cy * g.gx + cx;
             if (PASS == 0) {
-                atomicAdd(&cell_count_or_cursor[c], 1);
+                atomicAdd(&count_or_cursor[c], 1);
             } else {
-                int32_t pos = atomicAdd(&cell_count_or_cursor[c], 1);
-                cell_items[pos] = (int32_t)p;
+                int32_t pos = atomicAdd(&count_or_cursor[c], 1);
+                items[pos] = (int32_t)p;
             }
         }
+}
+__device__ __forceinline__ PartLite lite_of(const PartHeader &h) {
+    PartLite l;
+    l.xminf = __double2float_rd(h.xmin);
+    l.xmaxf = __double2float_ru(h.xmax);
+    l.yminf = (float)h.by0;    // exact: by0 is a float value
+    l.inv_hf = (float)h.inv_h;  // exact: inv_h is a float value
+    l.nb_flags = (h.n_buckets & 0x00ffffff) | ((h.flags & 1) ? (int32_t)0x80000000 : 0);
+    l.bucket_base = h.bucket_base;
+    return l;
+}
+// sort each cell's candidates ascending (first hit = lowest row; parts of one MultiPolygon row are
+// adjacent) and write the one-sector cell record
+__global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__restrict__ cell_start, int32_t *__restrict__ items,
+                              const PartHeader *__restrict__ parts, int64_t n_cells) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    int32_t a = cell_start[c], b = cell_start[c + 1];
+    for (int32_t i = a + 1; i < b; ++i) {
+        int32_t x = items[i], k = i - 1;
+        while (k >= a && items[k] > x) {
+            items[k + 1] = items[k];
+            --k;
+        }
+        items[k + 1] = x;
+    }
+    CellRec r;
+    r.count = b - a;
+    r.first = (b - a == 1) ? items[a] : a;
+    if (b > a) {
+        r.lite = lite_of(parts[items[a]]);
+    } else {
+        r.lite.xminf = r.lite.xmaxf = r.lite.yminf = r.lite.inv_hf = 0.0f;
+        r.lite.nb_flags = r.lite.bucket_base = 0;
+    }
+    cells[c] = r;
+}
+__global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_parts, PartRec *__restrict__ recs) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    PartHeader h = parts[p];
+    PartRec r;
+    r.lite = lite_of(h);
+    r.geom = h.geom;
+    r.pad = 0;
+    recs[p] = r;
+}
+__global__ void k_bucket_ranges(const int32_t *__restrict__ bstart, int2 *__restrict__ ranges, int64_t n) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b < n) ranges[b] = make_int2(bstart[b], bstart[b + 1]);
 }
 
 // edge slot c of ring [c0,c1): (c -> c+1), or the implicit closing edge geo's Polygon::new would add
@@ -251,8 +348,8 @@ __global__ void __launch_bounds__(256) k_buckets(int type, int64_t n_parts, cons
                 // holes may stick out of the exterior's bbox: only the part of their y-range inside the
                 // bucketed span [ymin,ymax] can hold a queried p.y (queries are bbox-filtered first)
                 if (yhi < h.ymin || ylo > h.ymax) continue;
-                int32_t b0 = mono_index(fmax(ylo, h.ymin), h.ymin, h.inv_h, h.n_buckets);
-                int32_t b1 = mono_index(fmin(yhi, h.ymax), h.ymin, h.inv_h, h.n_buckets);
+                int32_t b0 = mono_index(fmax(ylo, h.ymin), h.by0, h.inv_h, h.n_buckets);
+                int32_t b1 = mono_index(fmin(yhi, h.ymax), h.by0, h.inv_h, h.n_buckets);
                 for (int32_t b = b0; b <= b1; ++b) {
                     if (PASS == 0) {
                         atomicAdd(&count_or_cursor[h.bucket_base + b], 1);
@@ -324,121 +421,286 @@ __global__ void k_materialise(int type, int64_t n_parts, const double2 *__restri
 // the query kernel
 // ------------------------------------------------------------------------------------------------
 struct IndexView {
-    const PartHeader *parts;
-    const GridParams *grid;
-    const int32_t *cell_start, *cell_items, *bucket_start;
+    const CellRec *cells;
+    const int32_t *cell_items;
+    const PartRec *parts;
+    const int2 *bucket_range;
     const EdgeRec *entries;
     const int32_t *entry_ring;
+    int32_t multi;  // polygon side is MULTIPOLYGON: several parts may share a row
+    GridParams grid;
 };
 
-// geo coord_pos_relative_to_ring edge rule; returns true when p is on this edge (boundary)
-__device__ __forceinline__ bool edge_rule(const EdgeRec &ed, double px, double py, int &wn) {
-    if (ed.sy <= py) {
-        if (ed.ey >= py) {
-            double o = orient2d(ed.sx, ed.sy, ed.ex, ed.ey, px, py);
-            if (o > 0.0 && ed.ey != py) wn += 1;
-            else if (o == 0.0 && value_in_between(px, ed.sx, ed.ex)) return true;
+// 256-bit loads (sm_100: LDG.E.256): one instruction, one L1 wavefront per distinct line
+__device__ __forceinline__ void ld256(const void *p, double &a, double &b, double &c, double &d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256(const void *p, int32_t (&r)[8]) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// One edge of geo's coord_pos_relative_to_ring loop, evaluated WITHOUT control flow: the orientation
+// determinant and its static filter (Shewchuk stage A) are computed for every listed edge (nine FP64
+// arithmetic ops, six compares) and the up/down rules are predicate arithmetic.  Whenever the filter
+// cannot certify a NON-ZERO sign on an edge that actually straddles p.y — which includes every
+// collinear (possible boundary) configuration — `undecided` is raised and the point is re-evaluated
+// with the exact adaptive predicate and geo's boundary rule (k_pip_deferred / bucket_contains_exact).
+// Probability ~1e-9 per edge on random data, so the hot loop has no branch, no call, no
+// adaptive-precision code.  The winding contribution is identical to geo's for every decided edge.
+__device__ __forceinline__ void edge_rule_fast(double sx, double sy, double ex, double ey, double px, double py, int &wn,
+                                               bool &undecided) {
+    const double dl = (sx - px) * (ey - py);
+    const double dr = (sy - py) * (ex - px);
+    const double det = dl - dr;
+    // three ordinate comparisons decide everything geo's nested ifs decide:
+    //   a = start.y <= p.y, b = end.y <= p.y, c = end.y >= p.y
+    //   upward rule acts   <=> a && c ; counts <=> a && !b (end.y > p.y) && det > 0
+    //   downward rule acts <=> !a && b ; counts <=> det < 0
+    const bool a = sy <= py, b = ey <= py, c = ey >= py;
+    const bool act = a ? c : b;
+    const bool certain = fabs(det) > kCcwA * (fabs(dl) + fabs(dr));  // strict: det == 0 is never "certain"
+    undecided = undecided || (act && !certain);
+    wn += (int)(a && !b && det > 0.0) - (int)(!a && b && det < 0.0);
+}
+// the same rule with the full adaptive predicate (exact sign always)
+__device__ __forceinline__ void edge_rule_exact(double sx, double sy, double ex, double ey, double px, double py, int &wn,
+                                                bool &boundary) {
+    if (sy <= py) {
+        if (ey >= py) {
+            double o = orient2d(sx, sy, ex, ey, px, py);
+            if (o > 0.0 && ey != py) wn += 1;
+            else if (o == 0.0 && value_in_between(px, sx, ex)) boundary = true;
         }
-    } else if (ed.ey <= py) {
-        double o = orient2d(ed.sx, ed.sy, ed.ex, ed.ey, px, py);
+    } else if (ey <= py) {
+        double o = orient2d(sx, sy, ex, ey, px, py);
         if (o < 0.0) wn -= 1;
-        else if (o == 0.0 && value_in_between(px, ed.sx, ed.ex)) return true;
+        else if (o == 0.0 && value_in_between(px, sx, ex)) boundary = true;
     }
-    return false;
 }
 
-__device__ __forceinline__ EdgeRec load_edge(const EdgeRec *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 a = __ldg(q), b = __ldg(q + 1);
-    EdgeRec r;
-    r.sx = a.x, r.sy = a.y, r.ex = b.x, r.ey = b.y;
-    return r;
-}
-
-// Polygon::contains(coord) over the entries of one bucket.
+// Polygon::contains(coord) over the entries [e0,e1) of one bucket, serial and exact: used for parts
+// with holes and for the (rare) points the fast filter could not decide.
 // No holes: Inside <=> not on any listed edge and winding != 0.
 // Holes: entries are grouped by ring (ascending); exterior must wind, every hole must not, and no
 // ring may have p on its boundary (geo: boundary of exterior or of a hole => not Inside).
-__device__ __forceinline__ bool part_contains(const IndexView &ix, const PartHeader &h, double px, double py) {
-    int32_t b = mono_index(py, h.ymin, h.inv_h, h.n_buckets);
-    int32_t e0 = __ldg(ix.bucket_start + h.bucket_base + b), e1 = __ldg(ix.bucket_start + h.bucket_base + b + 1);
-    if (e0 == e1) return false;
+static __device__ __noinline__ bool bucket_contains_exact(const EdgeRec *__restrict__ entries,
+                                                          const int32_t *__restrict__ entry_ring, bool holes, int32_t e0, int32_t e1,
+                                                          double px, double py) {
     int wn = 0;
-    if (!(h.flags & 1)) {
-        for (int32_t k = e0; k < e1; ++k) {
-            EdgeRec ed = load_edge(ix.entries + k);
-            if (edge_rule(ed, px, py, wn)) return false;
-        }
-        return wn != 0;
-    }
-    int32_t cur = __ldg(ix.entry_ring + e0);
+    bool boundary = false;
+    if (e0 == e1) return false;
+    int32_t cur = holes ? entry_ring[e0] : 0;
     if (cur != 0) return false;  // no exterior edge near p.y: winding 0 => Outside
+    bool ok = true;
     for (int32_t k = e0; k < e1; ++k) {
-        int32_t ring = __ldg(ix.entry_ring + k);
-        if (ring != cur) {
-            if (cur == 0 ? (wn == 0) : (wn != 0)) return false;
-            cur = ring;
-            wn = 0;
+        if (holes) {
+            int32_t ring = entry_ring[k];
+            if (ring != cur) {
+                ok = ok && (cur == 0 ? (wn != 0) : (wn == 0));
+                cur = ring;
+                wn = 0;
+            }
         }
-        EdgeRec ed = load_edge(ix.entries + k);
-        if (edge_rule(ed, px, py, wn)) return false;
+        EdgeRec ed = entries[k];
+        edge_rule_exact(ed.sx, ed.sy, ed.ex, ed.ey, px, py, wn, boundary);
     }
-    return cur == 0 ? (wn != 0) : (wn == 0);
+    ok = ok && (cur == 0 ? (wn != 0) : (wn == 0));
+    return ok && !boundary;
 }
 
-// MODE 0: first_id (+ optional count)   MODE 1: write every (point, polygon) pair at pair_off[i]
+#ifndef GPL_PIP_MINB
+#define GPL_PIP_MINB 3
+#endif
+constexpr int kQueryThreads = 256;
+constexpr int32_t kDeferred = -2;  // first_id marker: "the fast filter could not decide, see k_pip_deferred"
+
+__device__ __forceinline__ void unpack_lite(const int32_t *r, PartLite &l) {
+    l.xminf = __int_as_float(r[0]), l.xmaxf = __int_as_float(r[1]);
+    l.yminf = __int_as_float(r[2]), l.inv_hf = __int_as_float(r[3]);
+    l.nb_flags = r[4], l.bucket_base = r[5];
+}
+// x-range + y-bucket of one candidate part: false when no listed edge can act on p
+__device__ __forceinline__ bool candidate_range(const IndexView &ix, const PartLite &l, double px, double py, int32_t &e0,
+                                                int32_t &e1) {
+    const int32_t nb = l.nb_flags & 0x00ffffff;
+    const double t = (py - (double)l.yminf) * (double)l.inv_hf;
+    // x outside the (outward rounded) range, or t < 0 (p.y < yminf <= ymin), or t >= nb + 1 (p.y > ymax)
+    if (!(px >= (double)l.xminf && px <= (double)l.xmaxf) || t < 0.0 || !(t < (double)(nb + 1))) return false;
+    const int32_t b = min((int32_t)t, nb - 1);
+    const int2 range = __ldg(ix.bucket_range + l.bucket_base + b);
+    e0 = range.x, e1 = range.y;
+    return true;
+}
+
+// Serial walk of one bucket with the branch-free rule.  The loads of a batch of four edge records are
+// issued back to back BEFORE any of them is consumed (four 256-bit loads in flight per lane): the first
+// version let the compiler interleave load and use and paid one L2 round trip per edge.
+// Returns Polygon::contains for this part when `undecided` stays false.
+// HOLES: entries are grouped by ring (ascending ring index, 0 = exterior): exterior must wind, every
+// hole must not.
+template <bool HOLES>
+__device__ __forceinline__ bool bucket_walk(const IndexView &ix, int32_t e0, int32_t e1, double px, double py, bool &undecided) {
+    int wn = 0;
+    bool und = false, ok = true;
+    int32_t cur = 0;
+    if (HOLES) {
+        if (e0 == e1) return false;
+        cur = __ldg(ix.entry_ring + e0);
+        if (cur != 0) return false;  // no exterior edge near p.y: winding 0 => Outside
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int32_t k = e0; k < e1; k += 4) {
+        double r[4][4];
+        int32_t ring[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // padding record: start.y = +inf, end.y = +inf never satisfies a or b => acts on nothing
+            r[j][0] = r[j][1] = r[j][2] = r[j][3] = inf;
+            ring[j] = cur;
+            if (k + j < e1) {
+                ld256(ix.entries + k + j, r[j][0], r[j][1], r[j][2], r[j][3]);
+                if (HOLES) ring[j] = __ldg(ix.entry_ring + k + j);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (HOLES) {
+                if (ring[j] != cur) {
+                    ok = ok && (cur == 0 ? (wn != 0) : (wn == 0));
+                    cur = ring[j];
+                    wn = 0;
+                }
+            }
+            edge_rule_fast(r[j][0], r[j][1], r[j][2], r[j][3], px, py, wn, und);
+        }
+    }
+    undecided = undecided || und;
+    if (HOLES) return ok && (cur == 0 ? (wn != 0) : (wn == 0));
+    return wn != 0;
+}
+
+// MODE 0: first_id (+ optional count); undecided points get first_id = kDeferred and bump *n_deferred.
+// MODE 1: write every (point, polygon) pair at pair_off[i]; undecided candidates are resolved in place
+//         with the exact predicate (this mode is not the throughput path).
+//
+// One thread per point, 32 consecutive points per warp (coalesced 512-byte read, software-prefetched one
+// grid stride ahead so the HBM latency is off the dependent chain).  Per point:
+//   grid cell (arithmetic) -> CellRec: ONE 256-bit load = candidate count + first candidate's parameters
+//   x-range / y-bucket (arithmetic) -> (start,end) of the edge list: one 64-bit load
+//   edge records: 256-bit loads, four in flight, branch-free rule.
+// Further candidates of the cell (overlapping bboxes) and MULTIPOLYGON rows read one 32-byte PartRec each.
+// No function calls and no adaptive-precision code in MODE 0: the register budget stays at 64 with
+// four CTAs per SM.
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) k_pip_query(IndexView ix, const double2 *__restrict__ pts,
-                                                   const uint8_t *__restrict__ pts_validity, int64_t n_pts,
-                                                   int32_t *__restrict__ first_id, int32_t *__restrict__ count,
-                                                   const int64_t *__restrict__ pair_off, uint64_t *__restrict__ lhs,
-                                                   uint64_t *__restrict__ rhs, int64_t point_base) {
-    const GridParams g = *ix.grid;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pts; i += stride) {
-        double2 p = __ldcs(pts + i);  // read-once stream: do not pollute L1/L2 residency of the index
-        int32_t first = -1, cnt = 0;
-        int64_t w = MODE == 1 ? pair_off[i] : 0;
+__global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const IndexView ix, const double2 *__restrict__ pts,
+                                                                           const uint8_t *__restrict__ pts_validity,
+                                                                           int64_t n_pts, int32_t *__restrict__ first_id,
+                                                                           int32_t *__restrict__ count,
+                                                                           const int64_t *__restrict__ pair_off,
+                                                                           uint64_t *__restrict__ lhs, uint64_t *__restrict__ rhs,
+                                                                           int64_t point_base,
+                                                                           unsigned long long *__restrict__ n_deferred) {
+    const GridParams &g = ix.grid;
+    const int64_t stride = (int64_t)gridDim.x * kQueryThreads;
+    int64_t i = (int64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    double2 p_next = make_double2(0.0, 0.0);
+    if (i < n_pts) p_next = __ldcs(pts + i);  // read-once stream
+    for (; i < n_pts; i += stride) {
+        const double2 p = p_next;
+        if (i + stride < n_pts) p_next = __ldcs(pts + i + stride);
         bool ok = p.x >= g.x0 && p.x <= g.x1 && p.y >= g.y0 && p.y <= g.y1;  // false for NaN (empty point)
         if (ok && pts_validity) ok = bit_get(pts_validity, i);
+        int32_t first = -1, cnt = 0;
+        bool undecided = false;
+        int64_t w = MODE == 1 ? pair_off[i] : 0;
         if (ok) {
-            int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
-            int64_t c = (int64_t)cy * g.gx + cx;
-            int32_t k0 = __ldg(ix.cell_start + c), k1 = __ldg(ix.cell_start + c + 1);
+            const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
+            int32_t r[8];
+            ld256(ix.cells + ((int64_t)cy * g.gx + cx), r);
+            const int32_t n_cand = r[0], first_part = r[1];
             int32_t last_geom = -1;
-            for (int32_t k = k0; k < k1; ++k) {
-                int32_t part = __ldg(ix.cell_items + k);
-                const double2 *hp = reinterpret_cast<const double2 *>(ix.parts + part);
-                double2 lo = __ldg(hp), hi = __ldg(hp + 1);  // bbox: first sector of the header
-                if (p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y) continue;
-                double2 h1 = __ldg(hp + 2);
-                double h2 = __ldg(reinterpret_cast<const double *>(hp + 3));
-                PartHeader h;
-                h.xmin = lo.x, h.ymin = lo.y, h.xmax = hi.x, h.ymax = hi.y;
-                h.inv_h = h1.x;
-                h.n_buckets = (int32_t)(__double_as_longlong(h1.y) & 0xffffffffLL);
-                h.bucket_base = (int32_t)(__double_as_longlong(h1.y) >> 32);
-                h.geom = (int32_t)(__double_as_longlong(h2) & 0xffffffffLL);
-                h.flags = (int32_t)(__double_as_longlong(h2) >> 32);
-                if (h.geom == last_geom) continue;  // MultiPolygon::contains = any part; count rows once
-                if (part_contains(ix, h, p.x, p.y)) {
-                    last_geom = h.geom;
-                    if (MODE == 1) {
-                        lhs[w] = (uint64_t)(point_base + i);
-                        rhs[w] = (uint64_t)h.geom;
-                        ++w;
-                    } else {
-                        if (first < 0) first = h.geom;
-                        ++cnt;
-                        if (count == nullptr) break;  // only the first hit is wanted
+            for (int32_t c = 0; c < n_cand; ++c) {
+                int32_t part = first_part, geom;
+                PartLite lite;
+                if (c == 0 && !ix.multi) {
+                    unpack_lite(r + 2, lite);
+                    if (n_cand > 1) part = __ldg(ix.cell_items + first_part);
+                    geom = part;
+                } else {
+                    if (n_cand > 1) part = __ldg(ix.cell_items + first_part + c);
+                    int32_t q[8];
+                    ld256(ix.parts + part, q);
+                    unpack_lite(q, lite);
+                    geom = q[6];
+                }
+                if (geom == last_geom) continue;  // MultiPolygon::contains = any part; count rows once
+                int32_t e0, e1;
+                if (!candidate_range(ix, lite, p.x, p.y, e0, e1)) continue;
+                bool und = false;
+                bool inside = lite.nb_flags < 0 ? bucket_walk<true>(ix, e0, e1, p.x, p.y, und)
+                                                : bucket_walk<false>(ix, e0, e1, p.x, p.y, und);
+                if (und) {
+                    if (MODE == 0) {
+                        undecided = true;
+                        break;
                     }
+                    inside = bucket_contains_exact(ix.entries, ix.entry_ring, lite.nb_flags < 0, e0, e1, p.x, p.y);
+                }
+                if (!inside) continue;
+                last_geom = geom;
+                if (MODE == 1) {
+                    lhs[w] = (uint64_t)(point_base + i);
+                    rhs[w] = (uint64_t)geom;
+                    ++w;
+                } else {
+                    if (first < 0) first = geom;
+                    ++cnt;
+                    if (count == nullptr) break;  // only the first hit is wanted
                 }
             }
         }
         if (MODE == 0) {
+            if (undecided) {
+                first = kDeferred;
+                atomicAdd(n_deferred, 1ULL);
+            }
             __stcs(first_id + i, first);
             if (count) __stcs(count + i, cnt);
         }
+    }
+}
+
+// Exact re-evaluation of the points k_pip_query<0> marked kDeferred (those whose orientation filter
+// failed on an edge that mattered: collinear or within a few ulps of an edge).  Launched after every
+// query; exits immediately when the counter is zero.
+__global__ void __launch_bounds__(256) k_pip_deferred(const IndexView ix, const double2 *__restrict__ pts, int64_t n_pts,
+                                                      int32_t *__restrict__ first_id, int32_t *__restrict__ count,
+                                                      const unsigned long long *__restrict__ n_deferred) {
+    if (*n_deferred == 0ULL) return;
+    const GridParams &g = ix.grid;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+        if (first_id[i] != kDeferred) continue;
+        const double2 p = pts[i];
+        const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
+        const CellRec cell = ix.cells[(int64_t)cy * g.gx + cx];
+        int32_t first = -1, cnt = 0, last_geom = -1;
+        for (int32_t c = 0; c < cell.count; ++c) {
+            const int32_t part = cell.count == 1 ? cell.first : ix.cell_items[cell.first + c];
+            const PartRec rec = ix.parts[part];
+            if (rec.geom == last_geom) continue;
+            int32_t e0, e1;
+            if (!candidate_range(ix, rec.lite, p.x, p.y, e0, e1)) continue;
+            if (!bucket_contains_exact(ix.entries, ix.entry_ring, rec.lite.nb_flags < 0, e0, e1, p.x, p.y)) continue;
+            last_geom = rec.geom;
+            if (first < 0) first = rec.geom;
+            ++cnt;
+            if (count == nullptr) break;
+        }
+        first_id[i] = first;
+        if (count) count[i] = cnt;
     }
 }
 
@@ -453,9 +715,10 @@ __global__ void k_histogram(const int32_t *__restrict__ ids, int64_t n, unsigned
 
 static IndexView view_of(const gpl_pip_index *idx) {
     IndexView v;
-    v.parts = idx->parts, v.grid = idx->grid;
-    v.cell_start = idx->cell_start, v.cell_items = idx->cell_items, v.bucket_start = idx->bucket_start;
-    v.entries = idx->entries, v.entry_ring = idx->entry_ring;
+    v.cells = idx->cells, v.cell_items = idx->cell_overflow, v.parts = idx->parts;
+    v.bucket_range = idx->bucket_range, v.entries = idx->entries, v.entry_ring = idx->entry_ring;
+    v.multi = idx->multi ? 1 : 0;
+    v.grid = idx->grid;
     return v;
 }
 
@@ -468,9 +731,12 @@ static int query_grid(int64_t n) {
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
               int32_t *first_dev, int32_t *count_dev, cudaStream_t stream) {
     if (n == 0) return GPL_OK;
-    k_pip_query<0><<<query_grid(n), 256, 0, stream>>>(view_of(idx), reinterpret_cast<const double2 *>(pts_dev), validity_dev,
-                                                       n, first_dev, count_dev, nullptr, nullptr, nullptr, 0);
-    ctx->launches++;
+    const double2 *pts = reinterpret_cast<const double2 *>(pts_dev);
+    GPL_CUDA(cudaMemsetAsync(idx->n_deferred, 0, sizeof(unsigned long long), stream));
+    k_pip_query<0><<<query_grid(n), kQueryThreads, 0, stream>>>(view_of(idx), pts, validity_dev, n, first_dev, count_dev, nullptr,
+                                                                  nullptr, nullptr, 0, idx->n_deferred);
+    k_pip_deferred<<<kSMs * 4, 256, 0, stream>>>(view_of(idx), pts, n, first_dev, count_dev, idx->n_deferred);
+    ctx->launches += 2;
     GPL_CUDA(cudaGetLastError());
     return GPL_OK;
 }
@@ -479,19 +745,48 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
 
 using namespace gpl;
 
+// Keep the index slab resident in the 126 MB L2 while 1.6 GB of points stream past it: mark the slab
+// as a persisting access-policy window on the context stream (the point loads are ld.global.cs,
+// i.e. evict-first).  Best effort: failures only cost performance.
+static void l2_pin(gpl_pip_index *idx, bool on) {
+    gpl_ctx *ctx = idx->ctx;
+    static const bool enabled = []() {
+        const char *e = getenv("GPL_L2_PIN");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled || ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (on) {
+        size_t carve = std::min<size_t>(idx->slab_bytes, ctx->l2_persist_max);
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        size_t win = std::min<size_t>(idx->slab_bytes, ctx->l2_window_max);
+        attr.accessPolicyWindow.base_ptr = idx->slab;
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = win > 0 ? std::min(1.0f, (float)carve / (float)win) : 0.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ctx->l2_pinned = idx->slab;
+    } else {
+        if (ctx->l2_pinned != idx->slab) return;  // another index owns the window now
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        ctx->l2_pinned = nullptr;
+    }
+    (void)cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    (void)cudaGetLastError();
+}
+
 extern "C" void gpl_pip_index_free(gpl_pip_index *idx) {
     if (!idx) return;
-    gpl_ctx *c = idx->ctx;
-    c->release(idx->parts);
-    c->release(idx->grid);
-    c->release(idx->cell_start);
-    c->release(idx->cell_items);
-    c->release(idx->bucket_start);
-    c->release(idx->entries);
-    c->release(idx->entry_ring);
+    if (idx->slab) l2_pin(idx, false);
+    idx->ctx->release(idx->slab);
     delete idx;
 }
 extern "C" int64_t gpl_pip_index_bytes(const gpl_pip_index *idx) { return idx ? idx->bytes : 0; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip_index **out) {
     GPL_REQUIRE(ctx && polys && out, GPL_ERR_INVALID_ARG, "gpl_pip_index_build: NULL argument");
@@ -520,28 +815,31 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     } while (0)
 
     const double2 *xy = reinterpret_cast<const double2 *>(polys->xy);
-    int64_t Pa = P > 0 ? P : 1;
-    void *q;
-    TRYF(ctx->alloc(sizeof(PartHeader) * Pa, &q));
-    idx->parts = (PartHeader *)q;
-    TRYF(ctx->alloc(sizeof(GridParams), &q));
-    idx->grid = (GridParams *)q;
+    const int64_t Pa = P > 0 ? P : 1;
+    cudaStream_t st = ctx->stream;
 
-    Scratch<int32_t> parent, nb, base;
+    // ---- phase 1 (scratch): bboxes, grid, cell counts, bucket counts --------------------------------
+    Scratch<PartHeader> hdr;
+    Scratch<GridParams> gp;
+    Scratch<int32_t> parent, nb, base, cell_count, cell_start, bcount, bstart;
+    Scratch<int64_t> totals;
+    TRYF(hdr.get(ctx, (size_t)Pa));
+    TRYF(gp.get(ctx, 1));
     TRYF(nb.get(ctx, (size_t)Pa + 1));
     TRYF(base.get(ctx, (size_t)Pa + 1));
+    TRYF(totals.get(ctx, 4));
     const int32_t *parent_p = nullptr;
     if (type == GPL_MULTIPOLYGON) {
         TRYF(parent.get(ctx, (size_t)Pa));
         if (polys->n_geoms > 0) {
-            k_part_parent<<<(int)ceil_div(polys->n_geoms, 256), 256, 0, ctx->stream>>>(polys->n_geoms, polys->geom_off, parent.p);
+            k_part_parent<<<(int)ceil_div(polys->n_geoms, 256), 256, 0, st>>>(polys->n_geoms, polys->geom_off, parent.p);
             ctx->launches++;
         }
         parent_p = parent.p;
     }
-    int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Pa, 8), (int64_t)kSMs * 8));
-    k_part_headers<<<wgrid, 256, 0, ctx->stream>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off,
-                                                  polys->validity, parent_p, idx->parts, nb.p);
+    const int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Pa, 8), (int64_t)kSMs * 8));
+    k_part_headers<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, polys->validity,
+                                          parent_p, hdr.p, nb.p);
     ctx->launches++;
     CUDAF(cudaGetLastError());
 
@@ -549,88 +847,106 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     int64_t G = (int64_t)ceil(sqrt((double)Pa));
     if (G < 1) G = 1;
     if (G > 2048) G = 2048;
-    idx->gx = idx->gy = (int32_t)G;
-    k_grid_params<<<1, 1024, 0, ctx->stream>>>(idx->parts, P, idx->gx, idx->gy, idx->grid);
+    const int64_t n_cells = G * G;
+    k_grid_params<<<1, 1024, 0, st>>>(hdr.p, P, (int32_t)G, (int32_t)G, gp.p);
     ctx->launches++;
 
-    // cell lists: count -> scan -> fill -> sort
-    int64_t n_cells = G * G;
-    TRYF(ctx->alloc(sizeof(int32_t) * (n_cells + 1), &q));
-    idx->cell_start = (int32_t *)q;
-    Scratch<int32_t> cursor;
-    TRYF(cursor.get(ctx, (size_t)n_cells + 1));
-    CUDAF(cudaMemsetAsync(cursor.p, 0, sizeof(int32_t) * (n_cells + 1), ctx->stream));
+    TRYF(cell_count.get(ctx, (size_t)n_cells + 1));
+    TRYF(cell_start.get(ctx, (size_t)n_cells + 1));
+    CUDAF(cudaMemsetAsync(cell_count.p, 0, sizeof(int32_t) * (n_cells + 1), st));
     if (P > 0) {
-        k_cells<0><<<(int)ceil_div(P, 128), 128, 0, ctx->stream>>>(idx->parts, P, idx->grid, cursor.p, nullptr);
+        k_cells<0><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, nullptr);
         ctx->launches++;
     }
-    Scratch<int64_t> totals;
-    TRYF(totals.get(ctx, 4));
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, cursor.p, n_cells, idx->cell_start, totals.p)));
-    // bucket bases (no data dependence on the host: sum of n_buckets is bounded by P + n_coords/2)
+    TRYF((exclusive_scan<int32_t, int32_t>(ctx, cell_count.p, n_cells, cell_start.p, totals.p)));
+
+    // bucket bases and per-bucket entry counts (sum of n_buckets <= P + n_coords/2 + 1: no host round trip)
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, nb.p, P, base.p, totals.p + 1)));
     if (P > 0) {
-        k_set_bucket_base<<<(int)ceil_div(P, 256), 256, 0, ctx->stream>>>(idx->parts, base.p, P);
+        k_set_bucket_base<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, base.p, P);
         ctx->launches++;
     }
-    int64_t NB_cap = Pa + polys->n_coords / 2 + 1;
-    TRYF(ctx->alloc(sizeof(int32_t) * (NB_cap + 1), &q));
-    idx->bucket_start = (int32_t *)q;
-    Scratch<int32_t> bcursor;
-    TRYF(bcursor.get(ctx, (size_t)NB_cap + 1));
-    CUDAF(cudaMemsetAsync(bcursor.p, 0, sizeof(int32_t) * (NB_cap + 1), ctx->stream));
+    const int64_t NB_cap = Pa + polys->n_coords / 2 + 1;
+    TRYF(bcount.get(ctx, (size_t)NB_cap + 1));
+    TRYF(bstart.get(ctx, (size_t)NB_cap + 1));
+    CUDAF(cudaMemsetAsync(bcount.p, 0, sizeof(int32_t) * (NB_cap + 1), st));
     if (P > 0) {
-        k_buckets<0><<<wgrid, 256, 0, ctx->stream>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, idx->parts,
-                                                    bcursor.p, nullptr);
+        k_buckets<0><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p, nullptr);
         ctx->launches++;
     }
-    // total bucket count lives on the device; scanning the capped array is equivalent (tail counts are 0)
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, bcursor.p, NB_cap, idx->bucket_start, totals.p + 2)));
+    TRYF((exclusive_scan<int32_t, int32_t>(ctx, bcount.p, NB_cap, bstart.p, totals.p + 2)));
 
-    // the two data-dependent sizes: one small D2H (index build is once per join, not per point)
+    // the data-dependent sizes + the grid parameters: one small D2H (index build is once per join)
     int64_t h_tot[3];
-    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDAF(cudaStreamSynchronize(ctx->stream));
-    idx->n_cell_items = h_tot[0];
+    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, st));
+    CUDAF(cudaMemcpyAsync(&idx->grid, gp.p, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
+    CUDAF(cudaStreamSynchronize(st));
+    idx->n_overflow = h_tot[0];  // all cell items
     idx->n_buckets = h_tot[1];
     idx->n_entries = h_tot[2];
-    if (idx->n_entries >= (1LL << 31) || idx->n_cell_items >= (1LL << 31)) {
+    if (idx->n_entries >= (1LL << 31) || idx->n_overflow >= (1LL << 31)) {
         set_error("join index too large (%lld edge records, %lld cell items)", (long long)idx->n_entries,
-                  (long long)idx->n_cell_items);
+                  (long long)idx->n_overflow);
         return fail(GPL_ERR_UNSUPPORTED);
     }
+    idx->any_holes = polys->n_rings > P;
+    idx->multi = type == GPL_MULTIPOLYGON;
 
-    TRYF(ctx->alloc(sizeof(int32_t) * (idx->n_cell_items + 1), &q));
-    idx->cell_items = (int32_t *)q;
-    TRYF(ctx->alloc(sizeof(EdgeRec) * (idx->n_entries + 1), &q));
-    idx->entries = (EdgeRec *)q;
+    // ---- phase 2: one slab, filled in place ----------------------------------------------------------
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t o_cells = carve(sizeof(CellRec) * n_cells);
+    const size_t o_parts = carve(sizeof(PartRec) * Pa);
+    const size_t o_brange = carve(sizeof(int2) * (idx->n_buckets + 1));
+    const size_t o_entries = carve(sizeof(EdgeRec) * (idx->n_entries + 1));
+    const size_t o_items = carve(sizeof(int32_t) * (idx->n_overflow + 1));
+    const size_t o_ring = idx->any_holes ? carve(sizeof(int32_t) * (idx->n_entries + 1)) : 0;
+    const size_t o_defer = carve(sizeof(unsigned long long));
+    void *q = nullptr;
+    TRYF(ctx->alloc(off, &q));
+    idx->slab = (uint8_t *)q;
+    idx->slab_bytes = off;
+    idx->cells = (CellRec *)(idx->slab + o_cells);
+    idx->parts = (PartRec *)(idx->slab + o_parts);
+    idx->bucket_range = (int2 *)(idx->slab + o_brange);
+    idx->entries = (EdgeRec *)(idx->slab + o_entries);
+    idx->cell_overflow = (int32_t *)(idx->slab + o_items);
+    idx->entry_ring = idx->any_holes ? (int32_t *)(idx->slab + o_ring) : nullptr;
+    idx->n_deferred = (unsigned long long *)(idx->slab + o_defer);
+    idx->bytes = (int64_t)off;
+
     Scratch<int64_t> entry_edge;
     TRYF(entry_edge.get(ctx, (size_t)idx->n_entries + 1));
-
     if (P > 0) {
-        CUDAF(cudaMemcpyAsync(cursor.p, idx->cell_start, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_cells<1><<<(int)ceil_div(P, 128), 128, 0, ctx->stream>>>(idx->parts, P, idx->grid, cursor.p, idx->cell_items);
-        k_sort_segments<int32_t><<<(int)ceil_div(n_cells, 128), 128, 0, ctx->stream>>>(idx->cell_items, idx->cell_start, n_cells);
-        CUDAF(cudaMemcpyAsync(bcursor.p, idx->bucket_start, sizeof(int32_t) * NB_cap, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_buckets<1><<<wgrid, 256, 0, ctx->stream>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, idx->parts,
-                                                    bcursor.p, entry_edge.p);
-        int64_t nbk = idx->n_buckets > 0 ? idx->n_buckets : 1;
-        k_sort_segments<int64_t><<<(int)ceil_div(nbk, 128), 128, 0, ctx->stream>>>(entry_edge.p, idx->bucket_start, idx->n_buckets);
-        // holes anywhere?  (n_rings > n_parts)
-        idx->any_holes = polys->n_rings > P;
-        if (idx->any_holes) {
-            TRYF(ctx->alloc(sizeof(int32_t) * (idx->n_entries + 1), &q));
-            idx->entry_ring = (int32_t *)q;
-        }
-        k_materialise<<<wgrid, 256, 0, ctx->stream>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, idx->parts,
-                                                     idx->bucket_start, entry_edge.p, idx->entries, idx->entry_ring);
-        ctx->launches += 5;
+        CUDAF(cudaMemcpyAsync(cell_count.p, cell_start.p, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToDevice, st));  // cursors
+        k_cells<1><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, idx->cell_overflow);
+        ctx->launches++;
+    }
+    k_cell_finish<<<(int)ceil_div(n_cells, 128), 128, 0, st>>>(idx->cells, cell_start.p, idx->cell_overflow, hdr.p, n_cells);
+    ctx->launches++;
+    if (idx->n_buckets > 0) {
+        k_bucket_ranges<<<(int)ceil_div(idx->n_buckets, 256), 256, 0, st>>>(bstart.p, idx->bucket_range, idx->n_buckets);
+        ctx->launches++;
+    }
+    if (P > 0) {
+        k_part_recs<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, P, idx->parts);
+        CUDAF(cudaMemcpyAsync(bcount.p, bstart.p, sizeof(int32_t) * NB_cap, cudaMemcpyDeviceToDevice, st));  // cursors
+        k_buckets<1><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p,
+                                            entry_edge.p);
+        const int64_t nbk = idx->n_buckets > 0 ? idx->n_buckets : 1;
+        k_sort_segments<int64_t><<<(int)ceil_div(nbk, 128), 128, 0, st>>>(entry_edge.p, bstart.p, idx->n_buckets);
+        k_materialise<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bstart.p,
+                                             entry_edge.p, idx->entries, idx->entry_ring);
+        ctx->launches += 4;
         CUDAF(cudaGetLastError());
     }
-    idx->bytes = (int64_t)(sizeof(PartHeader) * Pa + sizeof(int32_t) * (n_cells + 1 + idx->n_cell_items + NB_cap + 1) +
-                           sizeof(EdgeRec) * idx->n_entries + (idx->any_holes ? sizeof(int32_t) * idx->n_entries : 0));
     // scratch used by the kernels above goes back to the cache only after they have run
-    CUDAF(cudaStreamSynchronize(ctx->stream));
+    CUDAF(cudaStreamSynchronize(st));
+    l2_pin(idx, true);
     *out = idx;
     return GPL_OK;
 #undef TRYF
@@ -715,8 +1031,8 @@ extern "C" int gpl_contains_join_pairs(gpl_ctx *ctx, const gpl_pip_index *idx, c
         GPL_TRY(dr.get(ctx, (size_t)total));
         pl = dl.p, pr = dr.p;
     }
-    k_pip_query<1><<<query_grid(n_points), 256, 0, ctx->stream>>>(view_of(idx), reinterpret_cast<const double2 *>(pdev), nullptr,
-                                                                  n_points, nullptr, nullptr, off.p, pl, pr, 0);
+    k_pip_query<1><<<query_grid(n_points), kQueryThreads, 0, ctx->stream>>>(view_of(idx), reinterpret_cast<const double2 *>(pdev), nullptr,
+                                                                      n_points, nullptr, nullptr, off.p, pl, pr, 0, nullptr);
     ctx->launches++;
     GPL_CUDA(cudaGetLastError());
     if (mem == GPL_HOST) {

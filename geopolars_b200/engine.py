@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import GPL_DEVICE, GPL_HOST, check
+from ._lib import GPL_DEVICE, GPL_HOST, check  # noqa: F401 (re-exported for bench.py)
 from .geoarrow import GeoArrowArray, GeometryType
 
 
