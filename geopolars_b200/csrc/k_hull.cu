@@ -1,0 +1,388 @@
+// k_hull.cu — GeoSeries::convex_hull (reference: geopolars/geopolars-geo/src/geoseries.rs:23-26, impl `todo!()`
+// at :196-198; py accessor py-geopolars/python/geopolars/internals/georust/geoseries.py:76-90).
+// Arithmetic restated from geo 0.27 convex_hull/{mod,qhull}.rs (recalled, see oracle/geo_oracle.c):
+//   hull = quick_hull(exterior coords incl. the closing duplicate); strict-CCW tests with the exact
+//   orient2d; farthest point by p_orth . (p - a) evaluated in f64 with separately rounded mul/add;
+//   output ring = [lower chain left->right, max, upper chain right->left, min, first again].
+//
+// B200 design: one warp per geometry.  The geometry's exterior coordinates are staged once into shared
+// memory (coalesced LDG.128), permuted in place there exactly like geo permutes its Vec, and the
+// recursion hull_set(a, b, slice) runs as an explicit stack machine whose control flow is warp-uniform:
+//   * farthest point: lanes stride over the slice, warp arg-max (value, then LAST index: Iterator::max_by);
+//   * partition by is_ccw: lanes evaluate the exact predicate for 32 elements at a time, __ballot_sync
+//     + popc give each element its destination (stable: trues keep their order at the front);
+//   * the second recursive call is a tail call, so a frame is pushed only for the first one.
+// Output rings have data-dependent length: pass 1 counts vertices per geometry, an exclusive scan turns
+// counts into ring offsets, pass 2 re-runs the same deterministic machine and writes coordinates.
+// Parity note: geo partitions with an unstable Hoare scheme, so the ORDER of elements inside a slice
+// differs from ours; that order only matters when two distinct points tie exactly for "farthest" —
+// then geo's pick depends on its slice order.  Tie-free inputs (and ties between identical
+// coordinates, e.g. the ring's closing duplicate) give bit-identical rings.  DESIGN.md "convex_hull".
+#include <math.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace gpl {
+
+constexpr int kHullWarps = 4;  // warps per CTA
+
+struct HullFrame {  // pending "emit far, then hull_set(a, far, slice)" after the first recursive call returns
+    double ax, ay;
+    int32_t start, len, far_pos, pad;
+};
+
+__device__ __forceinline__ bool lex_less(double2 a, double2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+__device__ __forceinline__ bool is_ccw(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
+
+// stable partition of P[s, s+len) by is_ccw(a, b, .): trues to the front (order kept), falses after
+// (order kept).  tmp is a scratch area of at least len elements.  Returns the number of trues.
+__device__ __forceinline__ int32_t partition_ccw(double2 *P, double2 *tmp, int32_t s, int32_t len, double2 a, double2 b, int lane) {
+    if (len <= 0) return 0;
+    int32_t n_true = 0, n_false = 0;
+    // pass 1: trues compacted into tmp[0..T), falses into tmp[len-1 .. ] from the back in REVERSE so that one
+    // pass suffices; pass 2 copies back, un-reversing the falses.
+    for (int32_t c = 0; c < len; c += 32) {
+        const int32_t i = c + lane;
+        const bool in = i < len;
+        double2 q = in ? P[s + i] : make_double2(0.0, 0.0);
+        const bool t = in && is_ccw(a, b, q);
+        const unsigned mt = __ballot_sync(0xffffffffu, t), mf = __ballot_sync(0xffffffffu, in && !t);
+        const unsigned below = (1u << lane) - 1u;
+        if (t) tmp[n_true + __popc(mt & below)] = q;
+        if (in && !t) tmp[len - 1 - (n_false + __popc(mf & below))] = q;
+        n_true += __popc(mt);
+        n_false += __popc(mf);
+    }
+    __syncwarp();
+    for (int32_t i = lane; i < len; i += 32) P[s + i] = i < n_true ? tmp[i] : tmp[len - 1 - (i - n_true)];
+    __syncwarp();
+    return n_true;
+}
+
+// index (within the slice) of the farthest point from segment a-b: max of p_orth . (p - a), LAST maximal element
+__device__ __forceinline__ int32_t farthest(const double2 *P, int32_t s, int32_t len, double2 a, double2 b, int lane) {
+    const double ox = a.y - b.y, oy = b.x - a.x;
+    double best = 0.0;
+    int32_t bi = -1;
+    for (int32_t i = lane; i < len; i += 32) {
+        const double2 q = P[s + i];
+        const double dx = q.x - a.x, dy = q.y - a.y;
+        const double v = ox * dx + oy * dy;
+        if (bi < 0 || !(v < best)) {  // max_by keeps the later element on ties
+            best = v;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        // lanes hold disjoint index sets: take the other if it is strictly better, or equal with a later index
+        const bool take = oi >= 0 && (bi < 0 || ov > best || (!(ov < best) && oi > bi));
+        if (take) {
+            best = ov;
+            bi = oi;
+        }
+    }
+    return bi;
+}
+
+template <bool WRITE>
+struct Emitter {
+    double2 *out;
+    int64_t n;
+    double2 first;
+    __device__ __forceinline__ void push(double2 p, int lane) {
+        if (n == 0) first = p;
+        if (WRITE && lane == 0) out[n] = p;
+        ++n;
+    }
+};
+
+// geo trivial_hull(points, include_on_hull = false) for fewer than four coordinates (lane-uniform, tiny)
+template <bool WRITE>
+__device__ __forceinline__ void trivial_hull(const double2 *P, int32_t n, Emitter<WRITE> &em, int lane) {
+    double2 ls[4];
+    int32_t m = n;
+    for (int32_t i = 0; i < n; ++i) ls[i] = P[i];
+    for (int32_t i = 1; i < m; ++i)  // sort_unstable_by(lex_cmp) on <= 3 items: any correct sort gives the same result
+        for (int32_t j = i; j > 0 && lex_less(ls[j], ls[j - 1]); --j) {
+            double2 t = ls[j];
+            ls[j] = ls[j - 1];
+            ls[j - 1] = t;
+        }
+    if (m == 3 && orient2d(ls[0].x, ls[0].y, ls[1].x, ls[1].y, ls[2].x, ls[2].y) == 0.0) {
+        ls[1] = ls[2];
+        m = 2;
+    }
+    if (m == 0) return;
+    if (m == 1) ls[m++] = ls[0];
+    if (!(ls[0].x == ls[m - 1].x && ls[0].y == ls[m - 1].y)) ls[m++] = ls[0];  // close
+    if (m >= 4) {  // make_ccw_winding: least index is 0 after the sort, prev = m-2, next = 1
+        if (orient2d(ls[m - 2].x, ls[m - 2].y, ls[0].x, ls[0].y, ls[1].x, ls[1].y) < 0.0) {
+            double2 t = ls[1];  // reverse [p0,p1,p2,p0] -> [p0,p2,p1,p0]
+            ls[1] = ls[m - 2];
+            ls[m - 2] = t;
+        }
+    }
+    for (int32_t i = 0; i < m; ++i) em.push(ls[i], lane);
+}
+
+// hull_set(a, b, P[s, s+len)) as a stack machine; emits vertices in geo's order
+template <bool WRITE>
+__device__ __forceinline__ void hull_set(double2 *P, double2 *tmp, HullFrame *stack, double2 a, double2 b, int32_t s, int32_t len,
+                                         Emitter<WRITE> &em, int lane) {
+    int32_t depth = 0;
+    for (;;) {
+        if (len >= 2) {
+            const int32_t fi = farthest(P, s, len, a, b, lane);
+            if (lane == 0) {  // swap_remove_to_first
+                double2 t = P[s];
+                P[s] = P[s + fi];
+                P[s + fi] = t;
+            }
+            __syncwarp();
+            const double2 far = P[s];
+            const int32_t s1 = s + 1, l1 = len - 1;
+            const int32_t k = partition_ccw(P, tmp, s1, l1, far, b, lane);
+            if (lane == 0) {
+                HullFrame f;
+                f.ax = a.x, f.ay = a.y, f.start = s1, f.len = l1, f.far_pos = s, f.pad = 0;
+                stack[depth] = f;
+            }
+            __syncwarp();
+            ++depth;
+            a = far;  // hull_set(far, b, P[s1, s1+k))
+            s = s1;
+            len = k;
+            continue;
+        }
+        if (len == 1) em.push(P[s], lane);
+        if (depth == 0) return;
+        --depth;
+        const HullFrame f = stack[depth];
+        const double2 far = P[f.far_pos];
+        em.push(far, lane);
+        const double2 fa = make_double2(f.ax, f.ay);
+        const int32_t k2 = partition_ccw(P, tmp, f.start, f.len, fa, far, lane);
+        a = fa;  // tail call hull_set(a, far, P[start, start+k2))
+        b = far;
+        s = f.start;
+        len = k2;
+    }
+}
+
+// number of exterior coordinates of geometry g and a gather of them into dst (CoordsIter::exterior_coords_iter)
+__device__ __forceinline__ int64_t exterior_count(int type, int64_t g, const int64_t *geom_off, const int64_t *part_off,
+                                                  const int64_t *ring_off) {
+    switch (type) {
+    case GPL_POINT: return 1;
+    case GPL_LINESTRING:
+    case GPL_MULTIPOINT: return geom_off[g + 1] - geom_off[g];
+    case GPL_MULTILINESTRING: return ring_off[geom_off[g + 1]] - ring_off[geom_off[g]];
+    case GPL_POLYGON: return geom_off[g + 1] > geom_off[g] ? ring_off[geom_off[g] + 1] - ring_off[geom_off[g]] : 0;
+    default: {
+        int64_t n = 0;
+        for (int64_t p = geom_off[g]; p < geom_off[g + 1]; ++p)
+            if (part_off[p + 1] > part_off[p]) n += ring_off[part_off[p] + 1] - ring_off[part_off[p]];
+        return n;
+    }
+    }
+}
+__device__ __forceinline__ void exterior_gather(int type, int64_t g, const double2 *__restrict__ xy, const int64_t *geom_off,
+                                                const int64_t *part_off, const int64_t *ring_off, double2 *dst, int lane) {
+    int64_t c0 = 0, c1 = 0;
+    switch (type) {
+    case GPL_POINT: c0 = g, c1 = g + 1; break;
+    case GPL_LINESTRING:
+    case GPL_MULTIPOINT: c0 = geom_off[g], c1 = geom_off[g + 1]; break;
+    case GPL_MULTILINESTRING: c0 = ring_off[geom_off[g]], c1 = ring_off[geom_off[g + 1]]; break;
+    case GPL_POLYGON:
+        if (geom_off[g + 1] > geom_off[g]) c0 = ring_off[geom_off[g]], c1 = ring_off[geom_off[g] + 1];
+        break;
+    default: {
+        int64_t o = 0;
+        for (int64_t p = geom_off[g]; p < geom_off[g + 1]; ++p) {
+            if (part_off[p + 1] <= part_off[p]) continue;
+            const int64_t a = ring_off[part_off[p]], b = ring_off[part_off[p] + 1];
+            for (int64_t c = a + lane; c < b; c += 32) dst[o + (c - a)] = __ldcs(xy + c);
+            o += b - a;
+        }
+        return;
+    }
+    }
+    for (int64_t c = c0 + lane; c < c1; c += 32) dst[c - c0] = __ldcs(xy + c);
+}
+
+// max exterior coordinate count over all geometries (sizes the per-warp staging area)
+__global__ void k_hull_max_len(int type, int64_t n_geoms, const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
+                               const int64_t *__restrict__ ring_off, unsigned long long *__restrict__ out) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (g < n_geoms) v = (unsigned long long)exterior_count(type, g, geom_off, part_off, ring_off);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+// One warp per geometry.  The staging area (points, scratch, frame stack) is in shared memory when the
+// largest geometry fits (cap_smem coordinates per warp), otherwise in a per-warp global workspace.
+template <bool WRITE>
+__global__ void __launch_bounds__(kHullWarps * 32) k_hull(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+                                                          const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
+                                                          const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
+                                                          int32_t cap, int use_smem, uint8_t *__restrict__ workspace,
+                                                          int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
+                                                          double2 *__restrict__ out_xy) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)cap * (2 * sizeof(double2) + sizeof(HullFrame));
+    uint8_t *base = use_smem ? smem + wid * per_warp : workspace + ((size_t)blockIdx.x * kHullWarps + wid) * per_warp;
+    double2 *P = reinterpret_cast<double2 *>(base);
+    double2 *tmp = P + cap;
+    HullFrame *stack = reinterpret_cast<HullFrame *>(tmp + cap);
+    const int64_t n_warps = (int64_t)gridDim.x * kHullWarps;
+    for (int64_t g = (int64_t)blockIdx.x * kHullWarps + wid; g < n_geoms; g += n_warps) {
+        Emitter<WRITE> em;
+        em.n = 0;
+        em.out = WRITE ? out_xy + out_off[g] : nullptr;
+        em.first = make_double2(0.0, 0.0);
+        if (bit_get(validity, g)) {
+            int32_t n = (int32_t)exterior_count(type, g, geom_off, part_off, ring_off);
+            __syncwarp();
+            exterior_gather(type, g, xy, geom_off, part_off, ring_off, P, lane);
+            __syncwarp();
+            if (n < 4) {
+                trivial_hull<WRITE>(P, n, em, lane);
+            } else {
+                // utils::least_and_greatest_index: FIRST least and FIRST greatest in lexicographic order
+                int32_t mi = -1, xi = -1;
+                double2 mn = make_double2(0.0, 0.0), mx = mn;
+                for (int32_t i = lane; i < n; i += 32) {
+                    const double2 q = P[i];
+                    if (mi < 0 || lex_less(q, mn)) mn = q, mi = i;
+                    if (xi < 0 || lex_less(mx, q)) mx = q, xi = i;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ox = __shfl_xor_sync(0xffffffffu, mn.x, o), oy = __shfl_xor_sync(0xffffffffu, mn.y, o);
+                    const int32_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    const double2 oq = make_double2(ox, oy);
+                    if (oi >= 0 && (mi < 0 || lex_less(oq, mn) || (!lex_less(mn, oq) && oi < mi))) mn = oq, mi = oi;
+                    const double px = __shfl_xor_sync(0xffffffffu, mx.x, o), py = __shfl_xor_sync(0xffffffffu, mx.y, o);
+                    const int32_t pi = __shfl_xor_sync(0xffffffffu, xi, o);
+                    const double2 pq = make_double2(px, py);
+                    if (pi >= 0 && (xi < 0 || lex_less(mx, pq) || (!lex_less(pq, mx) && pi < xi))) mx = pq, xi = pi;
+                }
+                int32_t min_idx = mi, max_idx = xi;
+                if (lane == 0) {  // swap_remove_to_first(min), then fix up max_idx exactly like geo
+                    double2 t = P[0];
+                    P[0] = P[min_idx];
+                    P[min_idx] = t;
+                }
+                __syncwarp();
+                if (max_idx == 0) max_idx = min_idx;
+                max_idx = max_idx > 0 ? max_idx - 1 : 0;
+                if (lane == 0) {
+                    double2 t = P[1];
+                    P[1] = P[1 + max_idx];
+                    P[1 + max_idx] = t;
+                }
+                __syncwarp();
+                const double2 pmin = P[0], pmax = P[1];
+                const int32_t s = 2, len = n - 2;
+                int32_t k = partition_ccw(P, tmp, s, len, pmax, pmin, lane);
+                hull_set<WRITE>(P, tmp, stack, pmax, pmin, s, k, em, lane);
+                em.push(pmax, lane);
+                k = partition_ccw(P, tmp, s, len, pmin, pmax, lane);
+                hull_set<WRITE>(P, tmp, stack, pmin, pmax, s, k, em, lane);
+                em.push(pmin, lane);
+                if (!(em.first.x == pmin.x && em.first.y == pmin.y)) em.push(em.first, lane);  // LineString::close
+            }
+        }
+        if (!WRITE && lane == 0) counts[g] = em.n;
+        __syncwarp();
+    }
+}
+
+__global__ void k_iota(int64_t *__restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+}  // namespace gpl
+
+using namespace gpl;
+
+extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **out) {
+    GPL_REQUIRE(ctx && in && out, GPL_ERR_INVALID_ARG, "gpl_convex_hull: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = in->n_geoms;
+    const double2 *xy = reinterpret_cast<const double2 *>(in->xy);
+    Scratch<unsigned long long> maxlen;
+    Scratch<int64_t> counts, total;
+    GPL_TRY(maxlen.get(ctx, 1));
+    GPL_TRY(counts.get(ctx, (size_t)n + 1));
+    GPL_TRY(total.get(ctx, 1));
+    GPL_CUDA(cudaMemsetAsync(maxlen.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (n > 0) GPL_LAUNCH(ctx, k_hull_max_len, (int)ceil_div(n, 256), 256, 0, in->type, n, in->geom_off, in->part_off, in->ring_off, maxlen.p);
+    unsigned long long h_max = 0;
+    GPL_CUDA(cudaMemcpyAsync(&h_max, maxlen.p, sizeof(h_max), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    GPL_REQUIRE(h_max < (1ULL << 30), GPL_ERR_UNSUPPORTED, "convex_hull: a geometry with %llu coordinates is too large", h_max);
+    const int32_t cap = (int32_t)std::max<unsigned long long>(h_max, 4);
+    const size_t per_warp = (size_t)cap * (2 * sizeof(double2) + sizeof(HullFrame));
+    const size_t smem_bytes = per_warp * kHullWarps;
+    const bool use_smem = smem_bytes <= 200 * 1024;
+    int grid;
+    Scratch<uint8_t> workspace;
+    if (use_smem) {
+        GPL_CUDA(cudaFuncSetAttribute(k_hull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem_bytes, 1)));
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), kHullWarps), (int64_t)kSMs * per_sm));
+    } else {
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), kHullWarps), (int64_t)kSMs * 2));
+        GPL_TRY(workspace.get(ctx, per_warp * kHullWarps * (size_t)grid));
+    }
+    const size_t dyn = use_smem ? smem_bytes : 0;
+    if (n > 0) {
+        k_hull<false><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
+                                                                   cap, use_smem ? 1 : 0, workspace.p, counts.p, nullptr, nullptr);
+        ctx->launches++;
+        GPL_CUDA(cudaGetLastError());
+    }
+    Scratch<int64_t> ring_off, geom_off;
+    GPL_TRY(ring_off.get(ctx, (size_t)n + 1));
+    GPL_TRY(geom_off.get(ctx, (size_t)n + 1));
+    GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
+    int64_t h_total = 0;
+    GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    Scratch<double> oxy;
+    GPL_TRY(oxy.get(ctx, (size_t)h_total * 2));
+    if (n > 0) {
+        k_hull<true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
+                                                                  cap, use_smem ? 1 : 0, workspace.p, nullptr, ring_off.p,
+                                                                  reinterpret_cast<double2 *>(oxy.p));
+        ctx->launches++;
+        GPL_CUDA(cudaGetLastError());
+    }
+    // geom_off = identity: geometry i owns ring i (a null input row becomes an empty, null polygon)
+    GPL_LAUNCH(ctx, k_iota, (int)ceil_div(n + 1, 256), 256, 0, geom_off.p, n + 1);
+    if (workspace.p) GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // workspace returns to the cache below
+    gpl_array *o = array_new(ctx, GPL_POLYGON);
+    o->n_geoms = n, o->n_rings = n, o->n_coords = h_total;
+    o->xy = oxy.take(), o->own_xy = true;
+    o->ring_off = ring_off.take(), o->own_ring = true;
+    o->geom_off = geom_off.take(), o->own_geom = true;
+    o->validity = in->validity;  // shared with the input
+    o->parent = const_cast<gpl_array *>(in);
+    array_retain(o->parent);
+    *out = o;
+    return GPL_OK;
+}

@@ -13,4 +13,3 @@ GPL_STUB(gpl_array_import_arrow, gpl_ctx *, const void *, const void *, gpl_arra
 GPL_STUB(gpl_array_export_arrow, gpl_ctx *, const gpl_array *, void *, void *)
 GPL_STUB(gpl_export_f64_arrow, const double *, const uint8_t *, int64_t, void *, void *)
 GPL_STUB(gpl_export_bool_arrow, const uint8_t *, const uint8_t *, int64_t, void *, void *)
-GPL_STUB(gpl_convex_hull, gpl_ctx *, const gpl_array *, gpl_array **)
