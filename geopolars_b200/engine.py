@@ -125,6 +125,32 @@ class Context:
         d._keepalive = keepalive
         return d
 
+    def import_arrow(self, arr) -> "DeviceArray":
+        """pyarrow geometry array (geoarrow nested layout or WKB binary) -> HBM, through the Arrow C Data
+        Interface exactly like py-geopolars/src/ffi.rs:12-32 (`_export_to_c` into ArrowArray/ArrowSchema)."""
+        import pyarrow as pa
+
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()  # the reference rechunks to one chunk first (ffi.rs:56)
+        c_array = (C.c_uint8 * 80)()   # struct ArrowArray
+        c_schema = (C.c_uint8 * 72)()  # struct ArrowSchema
+        arr._export_to_c(C.addressof(c_array), C.addressof(c_schema))
+        h = C.c_void_p()
+        try:
+            check(self.lib.gpl_array_import_arrow(self._h, C.addressof(c_array), C.addressof(c_schema), C.byref(h)))
+        finally:
+            # import borrows: hand the structs back to pyarrow so that their release callbacks run
+            pa.Array._import_from_c(C.addressof(c_array), C.addressof(c_schema))
+        return DeviceArray(self, h)
+
+    def from_wkb(self, wkb) -> "DeviceArray":
+        """list of WKB bytes (None = null) or a pyarrow binary array, decoded once (util.rs:27-37 decodes per op)"""
+        import pyarrow as pa
+
+        if not isinstance(wkb, (pa.Array, pa.ChunkedArray)):
+            wkb = pa.array(list(wkb), type=pa.binary())
+        return self.import_arrow(wkb)
+
     def __del__(self):
         try:
             self.close()
@@ -168,6 +194,29 @@ class DeviceArray:
             if valid.all():
                 valid = None
         return GeoArrowArray(t, xy, geom_off=geom, part_off=part, ring_off=ring, valid=valid)
+
+    def to_arrow(self):
+        """HBM -> pyarrow geoarrow array through the Arrow C Data Interface (ffi.rs:36-49 in reverse)."""
+        import pyarrow as pa
+
+        c_array = (C.c_uint8 * 80)()
+        c_schema = (C.c_uint8 * 72)()
+        check(self.ctx.lib.gpl_array_export_arrow(self.ctx._h, self._h, C.addressof(c_array), C.addressof(c_schema)))
+        return pa.Array._import_from_c(C.addressof(c_array), C.addressof(c_schema))
+
+    def to_wkb(self):
+        """ISO WKB (little endian) per row as a pyarrow binary array (from_geom_vec, util.rs:11-24)."""
+        import pyarrow as pa
+
+        n = len(self)
+        off = np.zeros(n + 1, dtype=np.int32)
+        nbytes = C.c_int64(0)
+        check(self.ctx.lib.gpl_array_to_wkb(self.ctx._h, self._h, _np_ptr(off), None, C.byref(nbytes)))
+        buf = np.empty(max(nbytes.value, 1), dtype=np.uint8)
+        check(self.ctx.lib.gpl_array_to_wkb(self.ctx._h, self._h, _np_ptr(off), _np_ptr(buf), C.byref(nbytes)))
+        host = self.to_host()
+        validity = None if host.valid is None else pa.py_buffer(np.packbits(host.valid, bitorder="little").tobytes())
+        return pa.Array.from_buffers(pa.binary(), n, [validity, pa.py_buffer(off.tobytes()), pa.py_buffer(buf[: nbytes.value].tobytes())])
 
     def free(self) -> None:
         if getattr(self, "_h", None) and self.ctx._h:

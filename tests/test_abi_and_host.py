@@ -1,0 +1,70 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/geopolars_b200.h declares
+(no compute without a GPU), the product fails loudly without a device, and the host-side logic."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from geopolars_b200 import GeoArrowArray, GeometryType, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "geopolars_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported by libgeopolars_b200.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in geopolars_b200/_lib.py"
+    assert set(_lib.SIGNATURES) <= set(names)
+    assert lib.gpl_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from geopolars_b200.engine import Context
+
+    with pytest.raises(_lib.GeopolarsError) as e:
+        Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "geopolars_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                for line in open(os.path.join(dirpath, f), errors="replace"):
+                    code = line.split("//")[0].split("#", 1)[0] if f.endswith(".py") else line.split("//")[0]
+                    if f.endswith(".py"):
+                        assert not re.search(r"\b(import|from)\s+oracle\b", code), (f, line)
+                    else:
+                        assert not (code.lstrip().startswith("#include") and "oracle" in code), (f, line)
+                    assert "libgeo_oracle" not in code, (f, line)
+
+
+def test_geoarrow_container_and_row_sharding():
+    sq = [(0, 0), (1, 0), (1, 1), (0, 1), (0, 0)]
+    mp = GeoArrowArray.from_shapes(GeometryType.MULTIPOLYGON, [[[sq], [sq, sq]], [], [[sq]], None])
+    assert len(mp) == 4 and mp.n_parts == 3 and mp.n_rings == 4 and mp.n_coords == 20
+    assert mp.valid.tolist() == [True, True, True, False]
+    part = mp.take_rows(2, 4)
+    assert len(part) == 2 and part.geom_off.tolist() == [0, 1, 1] and part.ring_off.tolist() == [0, 5]
+    assert np.array_equal(part.xy, np.array(sq, float))
+    with pytest.raises(ValueError):
+        GeoArrowArray(GeometryType.POLYGON, np.zeros((0, 2)))
+    from geopolars_b200 import engine
+
+    assert engine._origin("Centroid")[0] == 0 and engine._origin((1, 2)) == (2, 1.0, 2.0) and engine._origin({"x": 3, "y": 4})[1:] == (3.0, 4.0)
+    with pytest.raises(ValueError):
+        engine._origin("middle")

@@ -1,0 +1,162 @@
+"""CPU tests of the oracle: pinned against the reference's golden vector, its bundled fixtures
+(SURVEY.md Appendix A soft values) and the exact-rational referee.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_close
+from geopolars_b200 import GeoArrowArray, GeometryType, synth
+from wkbutil import column_to_shapes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    code, shapes = column_to_shapes(z["offsets"], z["bytes"])
+    return GeoArrowArray.from_shapes(GeometryType(code), shapes), z
+
+
+def test_reference_golden_contains_vector(og, conv):
+    """geopolars/src/spatial_index.rs:432-484: exactly rows 1 and 2 of the 9 points are contained;
+    (0,10) lies on the boundary and is NOT contained; inner join (2,4), left join (9,4)."""
+    z = np.load(os.path.join(GOLD, "contains_golden.npz"))
+    sq = z["square"].tolist()
+    poly = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[sq + [sq[0]]]])  # polygon![] closes the ring
+    first, cnt = og.contains_join(conv(poly), z["points"], use_grid=True)
+    assert np.nonzero(first >= 0)[0].tolist() == z["inner_rows"].tolist()
+    assert int(cnt.sum()) == int(z["inner_shape"][0]) and len(first) == int(z["left_shape"][0])
+    pos = [og.coord_position(conv(poly), 0, *p) for p in z["points"]]
+    assert pos == [1, 2, 2, 0, 0, 0, 0, 0, 1]  # B I I O O O O O B
+    # unclosed ring given directly: geo's Polygon::new closes it, the oracle emulates that
+    open_poly = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[sq]])
+    first2, _ = og.contains_join(conv(open_poly), z["points"], use_grid=False)
+    assert np.array_equal(first, first2)
+
+
+def test_config1_cities_points(og, conv):
+    """BASELINE config 1: centroid(points) == points bit-exactly, area == 0, 202 rows"""
+    arr, _ = load("cities")
+    assert len(arr) == 202 and arr.type == GeometryType.POINT
+    c, v = og.centroid(conv(arr))
+    assert v.all() and np.array_equal(c, arr.xy)
+    assert np.array_equal(og.area(conv(arr)), np.zeros(202))
+    arr2, _ = load("naturalearth_cities")
+    assert len(arr2) == 243  # py-geopolars/tests/unit/internals/test_geoseries.py:4-5
+
+
+def test_fixture_soft_known_values(og, conv):
+    """SURVEY.md Appendix A (derived, not reference assertions): areas/centroids/envelopes to 1e-9"""
+    nybb, z = load("nybb")
+    assert nybb.type == GeometryType.MULTIPOLYGON and len(nybb) == 5
+    area = og.area(conv(nybb))
+    want_area = [1623821996.706837, 3045213694.3233314, 1937478349.33195, 636471237.9668642, 1186926294.336624]
+    assert rel_close(area, want_area, 1e-9)
+    assert np.all(np.abs(area / z["Shape_Area"] - 1) < 2e-6)  # the attribute column was computed upstream at lower precision
+    cen, v = og.centroid(conv(nybb))
+    want_cen = [(941639.4503875433, 150931.9911411282), (1034578.0784064498, 197116.6042299129), (998769.1146889547, 174169.76072686614),
+                (993336.964938482, 222451.43672456007), (1021174.7897672353, 249937.9800696837)]
+    assert v.all() and rel_close(cen, want_cen, 1e-9)
+    env, _ = og.envelope(conv(nybb))
+    assert env[0].tolist() == [913175.1090087891, 120121.8812543372, 970570.1481933594, 175708.9620361328]
+    low, _ = load("naturalearth_lowres")
+    assert len(low) == 177
+    a = og.area(conv(low))
+    assert rel_close(a[:4], [1.639510995900778, 76.30196359087157, 8.603984207472145, 1712.9952276493766], 1e-9)
+    c, _ = og.centroid(conv(low))
+    assert rel_close(c[1], (34.752989854755945, -6.25773242850609), 1e-9)
+
+
+def test_orient2d_sign_against_exact_rational(og):
+    from oracle import exact
+
+    rng = np.random.default_rng(1)
+    before = og.adapt_calls()
+    bad = 0
+    for k in range(4000):
+        a = rng.uniform(-1e3, 1e3, 2)
+        b = a + rng.uniform(-1, 1, 2) * 10.0 ** rng.integers(-6, 4)
+        t = rng.uniform(-2, 3)
+        c = a + t * (b - a)  # nearly collinear: the fast filter cannot decide
+        if k % 3 == 0:
+            c = np.nextafter(c, c + rng.normal(size=2))
+        if k % 50 == 0:
+            c = a.copy()  # exactly degenerate
+        got = og.orient2d(a, b, c)
+        want = exact.orient_sign(tuple(a), tuple(b), tuple(c))
+        bad += ((got > 0) - (got < 0)) != want
+    assert bad == 0
+    assert og.adapt_calls() > before + 200  # the adaptive stages really ran
+
+
+def test_contains_and_intersects_against_exact_rational(og, conv):
+    from oracle import exact
+
+    xy, ro, go = synth.star_polygons(9, 3)
+    polys = GeoArrowArray.polygons(xy, ro, go)
+    pts = np.concatenate([synth.uniform_points(1500, scale=30.0), xy[:40], 0.5 * (xy[:40] + xy[1:41])])
+    first, cnt = og.contains_join(conv(polys), pts, use_grid=True)
+    for i, p in enumerate(pts):
+        want = [j for j in range(9) if exact.polygon_contains(tuple(p), [xy[ro[j] : ro[j + 1]].tolist()])]
+        assert cnt[i] == len(want) and first[i] == (want[0] if want else -1)
+    axy, aoff = synth.walk_linestrings(300, 8, stream=3)
+    bxy, boff = synth.walk_linestrings(300, 8, stream=4, other_of=3)
+    A, B = GeoArrowArray.linestrings(axy, aoff), GeoArrowArray.linestrings(bxy, boff)
+    got = og.intersects_rowwise(conv(A), conv(B))
+    want = [exact.linestrings_intersect(axy[aoff[i] : aoff[i + 1]].tolist(), bxy[boff[i] : boff[i + 1]].tolist()) for i in range(300)]
+    assert got.tolist() == want and 50 < sum(want) < 250
+    d = og.distance_rowwise(conv(A), conv(B))
+    assert np.array_equal(d == 0.0, got)
+
+
+def test_convex_hull_against_exact_rational_and_scipy(og, conv):
+    from oracle import exact
+
+    xy, ro, go = synth.blob_polygons(60, 48)
+    arr = GeoArrowArray.polygons(xy, ro, go)
+    off, hxy = og.convex_hull(conv(arr))
+    from scipy.spatial import ConvexHull
+
+    for i in range(60):
+        ring = hxy[off[i] : off[i + 1]]
+        pts = xy[ro[i] : ro[i + 1]]
+        want = exact.convex_hull_vertices(pts.tolist())
+        assert np.array_equal(ring[0], ring[-1])
+        assert sorted(map(tuple, ring[:-1].tolist())) == sorted(want)
+        sp = ConvexHull(pts[:-1])
+        assert sorted(map(tuple, pts[:-1][sp.vertices].tolist())) == sorted(want)
+    # geo's documented vertex order on the 9-point example
+    ex = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[[(0, 0), (2, -1), (4, 0), (5, 2), (4, 4), (2, 5), (0, 4), (-1, 2), (0, 0)]]])
+    off, hxy = og.convex_hull(conv(ex))
+    assert hxy.tolist() == [[0, 0], [2, -1], [4, 0], [5, 2], [4, 4], [2, 5], [0, 4], [-1, 2], [0, 0]]
+
+
+def test_area_centroid_analytic_shapes(og, conv):
+    n = np.arange(3, 40)
+    shapes = []
+    for k in n:
+        th = 2 * np.pi * np.arange(k) / k
+        ring = [(3 + 2 * np.cos(t), -1 + 2 * np.sin(t)) for t in th]
+        shapes.append([ring + [ring[0]]])
+    arr = GeoArrowArray.from_shapes(GeometryType.POLYGON, shapes)
+    want = 0.5 * n * 4.0 * np.sin(2 * np.pi / n)
+    assert rel_close(og.area(conv(arr)), want, 1e-12)
+    c, v = og.centroid(conv(arr))
+    assert v.all() and np.allclose(c, [3, -1], atol=1e-12)
+    sq, hole = [(0, 0), (4, 0), (4, 4), (0, 4), (0, 0)], [(1, 1), (1, 2), (2, 2), (2, 1), (1, 1)]
+    p = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[sq, hole], [sq, sq], [[(0, 0), (2, 2), (4, 4), (0, 0)]], []])
+    assert og.area(conv(p)).tolist() == [15.0, 0.0, 0.0, 0.0]
+    c, v = og.centroid(conv(p))
+    assert v.tolist() == [True, True, True, False]
+    assert np.allclose(c[0], [(32 - 1.5) / 15, (32 - 1.5) / 15])
+    assert np.allclose(c[1], [2, 2]) and np.allclose(c[2], [2, 2])  # linestring fallbacks
+
+
+def test_synth_generators_are_bit_reproducible(og):
+    p = synth.uniform_points(5000, first=123)
+    assert np.array_equal(p, og.gen_uniform_points(2, 123, 5000, 1000.0))
+    xy, ro, go = synth.star_polygons(50, 10)
+    assert xy.shape == (50 * 65, 2) and np.array_equal(xy[ro[:-1]], xy[ro[1:] - 1])
+    a = og.area(og.OGArray(og.POLYGON, xy, geom_off=go, ring_off=ro))
+    assert (a > 10).all() and (a < 80).all()
