@@ -177,8 +177,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=100_000_000, help="points per GPU (BASELINE configs[1]: 100M)")
-    ap.add_argument("--ref-sample", type=int, default=8_000_000, help="points per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="points of the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=64_000_000, help="points per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=32_000_000, help="points of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--prebuilt-index", action="store_true", help="exclude the polygon index build from the step")
