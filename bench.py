@@ -85,7 +85,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -131,7 +131,10 @@ def cpu_baseline_sample(n_sample: int, threads: int = 0):
     xy, ro, go = synth.star_polygons(N_POLYGONS, POLY_GRID, 10.0, N_VERT)
     polys = og.OGArray(og.POLYGON, xy, geom_off=go, ring_off=ro)
     pts = og.gen_uniform_points(2, 0, n_sample, 1000.0)
-    cores = og.max_threads() if threads <= 0 else threads
+    if threads <= 0:
+        # every core this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = threads
     og.contains_join(polys, pts[: min(n_sample, 100_000)], True, threads)  # warm-up (page-in, thread pool)
     t0 = time.perf_counter()
     first, _ = og.contains_join(polys, pts, True, threads)
@@ -248,15 +251,15 @@ def main():
                 E.check(ctx.lib.gpl_join_histogram(ctx._h, ids.data_ptr(), n, counts.data_ptr(), N_POLYGONS, E.GPL_DEVICE))
                 dist.all_reduce(counts)
 
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample period
         for _ in range(max(args.warmup, 3)):
             step(False)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         launches0 = ctx.launch_count
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record(stream)
