@@ -80,6 +80,10 @@ struct __align__(32) CellRec {
 };
 static_assert(sizeof(CellRec) == 32, "CellRec must be one sector");
 
+constexpr int32_t kFastBit = 1 << 30;  // PartLite::nb_flags: the CellRec points at the FP32 fast table
+constexpr int kFastCShift = 24;        // bits 24..29: C/2 (C = 16-byte records per bucket incl. header, even)
+constexpr int kFastMaxC = 64;
+
 struct __align__(32) EdgeRec {  // one L2 sector
     double sx, sy, ex, ey;
 };
@@ -106,9 +110,14 @@ struct gpl_pip_index {
     int2 *bucket_range = nullptr;     // n_buckets: (start, end) into entries[]
     gpl::EdgeRec *entries = nullptr;
     int32_t *entry_ring = nullptr;    // ring index within part (0 = exterior), only if any part has holes
+    float4 *fast = nullptr;           // FP32 fixed-stride bucket table of the plain parts (see FastTable below)
+    int64_t n_fast = 0;               // 16-byte records in `fast`
+    size_t hot_bytes = 0;             // leading part of the slab the L2 persisting window covers (0 = all)
     bool multi = false;               // MULTIPOLYGON: parts[].geom differs from the part id
     bool any_holes = false;
     unsigned long long *n_deferred = nullptr;  // device counter inside the slab
+    uint32_t *deferred_list = nullptr;         // indices of deferred points (grown on demand)
+    uint32_t deferred_cap = 0;
     int64_t bytes = 0;
 };
 
@@ -264,7 +273,8 @@ __device__ __forceinline__ PartLite lite_of(const PartHeader &h) {
 // sort each cell's candidates ascending (first hit = lowest row; parts of one MultiPolygon row are
 // adjacent) and write the one-sector cell record
 __global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__restrict__ cell_start, int32_t *__restrict__ items,
-                              const PartHeader *__restrict__ parts, int64_t n_cells) {
+                              const PartHeader *__restrict__ parts, const int32_t *__restrict__ fast_c,
+                              const int32_t *__restrict__ fast_base, int64_t n_cells) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     int32_t a = cell_start[c], b = cell_start[c + 1];
@@ -281,6 +291,10 @@ __global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__rest
     r.first = (b - a == 1) ? items[a] : a;
     if (b > a) {
         r.lite = lite_of(parts[items[a]]);
+        if (b - a == 1 && fast_c[items[a]] > 0) {  // the one-load fast path: parameters of the FP32 table
+            r.lite.nb_flags |= kFastBit | ((fast_c[items[a]] / 2) << kFastCShift);
+            r.lite.bucket_base = fast_base[items[a]];
+        }
     } else {
         r.lite.xminf = r.lite.xmaxf = r.lite.yminf = r.lite.inv_hf = 0.0f;
         r.lite.nb_flags = r.lite.bucket_base = 0;
@@ -297,6 +311,65 @@ __global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_part
     r.pad = 0;
     recs[p] = r;
 }
+// ---- FP32 fast table --------------------------------------------------------------------------------
+// The query kernel is bound by the number of 32-byte L2 sectors it pulls per point (measured: 7.5
+// sectors/point at ~90 % of the L2->SM bandwidth), so plain parts (no holes, POLYGON rows, short bucket
+// lists) get a second, denser table:
+//   * edges as four FLOATS relative to the part origin O = (xminf, yminf): 16 bytes, two per sector;
+//   * fixed stride: bucket b of a part starts at fast_base + b*C records, record 0 is a header {count},
+//     unused slots hold an inert sentinel (+inf ordinates) — no (start,end) lookup at all.
+// The floats only feed a FILTER with a rigorous error bound (fast_edge_rule); anything it cannot
+// certify is re-evaluated from the f64 records by the exact kernel.  kFastBit/kFastCShift live in
+// PartLite::nb_flags of the CellRec of a single-candidate cell.
+
+// per part: C (0 = not eligible) and number of 16-byte records
+__global__ void k_fast_plan(int type, const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ bcount,
+                            int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    PartHeader h = parts[p];
+    int32_t c = 0;
+    if (type == GPL_POLYGON && (h.flags & 2) && !(h.flags & 1)) {
+        int32_t mx = 0;
+        for (int32_t b = 0; b < h.n_buckets; ++b) mx = max(mx, bcount[h.bucket_base + b]);
+        c = (mx + 1 + 1) & ~1;  // header + edges, rounded up to an even number of 16-byte records
+        if (c > kFastMaxC) c = 0;
+    }
+    fast_c[p] = c;
+    fast_slots[p] = c * h.n_buckets;
+}
+// one warp per part: write header / float edges / sentinels of every bucket
+__global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict__ parts, int64_t n_parts,
+                                                   const int32_t *__restrict__ fast_c, const int32_t *__restrict__ fast_base,
+                                                   const int32_t *__restrict__ bstart, const EdgeRec *__restrict__ entries,
+                                                   float4 *__restrict__ fast) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    for (int64_t p = warp; p < n_parts; p += nwarps) {
+        const int32_t c = fast_c[p];
+        if (c == 0) continue;
+        const PartHeader h = parts[p];
+        const double ox = (double)__double2float_rd(h.xmin), oy = h.by0;
+        for (int32_t t = lane; t < c * h.n_buckets; t += 32) {
+            const int32_t b = t / c, k = t - b * c;
+            const int32_t e0 = bstart[h.bucket_base + b], n = bstart[h.bucket_base + b + 1] - e0;
+            float4 r;
+            if (k == 0) {
+                r = make_float4(__int_as_float(n), 0.0f, 0.0f, 0.0f);
+            } else if (k <= n) {
+                const EdgeRec ed = entries[e0 + k - 1];
+                r = make_float4(__double2float_rn(ed.sx - ox), __double2float_rn(ed.sy - oy), __double2float_rn(ed.ex - ox),
+                                __double2float_rn(ed.ey - oy));
+            } else {
+                r = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
+            }
+            fast[(int64_t)fast_base[p] + t] = r;
+        }
+    }
+}
+
 __global__ void k_bucket_ranges(const int32_t *__restrict__ bstart, int2 *__restrict__ ranges, int64_t n) {
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b < n) ranges[b] = make_int2(bstart[b], bstart[b + 1]);
@@ -427,13 +500,21 @@ struct IndexView {
     const int2 *bucket_range;
     const EdgeRec *entries;
     const int32_t *entry_ring;
+    const float4 *fast;
     int32_t multi;  // polygon side is MULTIPOLYGON: several parts may share a row
     GridParams grid;
 };
 
 // 256-bit loads (sm_100: LDG.E.256): one instruction, one L1 wavefront per distinct line
+#ifndef GPL_PIP_NOALLOC
+#define GPL_PIP_NOALLOC 0
+#endif
 __device__ __forceinline__ void ld256(const void *p, double &a, double &b, double &c, double &d) {
+#if GPL_PIP_NOALLOC
+    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#endif
 }
 __device__ __forceinline__ void ld256(const void *p, int32_t (&r)[8]) {
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -513,7 +594,10 @@ static __device__ __noinline__ bool bucket_contains_exact(const EdgeRec *__restr
 #ifndef GPL_PIP_MINB
 #define GPL_PIP_MINB 3
 #endif
-constexpr int kQueryThreads = 256;
+#ifndef GPL_PIP_THREADS
+#define GPL_PIP_THREADS 256
+#endif
+constexpr int kQueryThreads = GPL_PIP_THREADS;
 constexpr int32_t kDeferred = -2;  // first_id marker: "the fast filter could not decide, see k_pip_deferred"
 
 __device__ __forceinline__ void unpack_lite(const int32_t *r, PartLite &l) {
@@ -581,6 +665,75 @@ __device__ __forceinline__ bool bucket_walk(const IndexView &ix, int32_t e0, int
     return wn != 0;
 }
 
+// ---- FP32 filter walk over the fixed-stride fast table ----------------------------------------------
+// All quantities are relative to the part origin O = (xminf, yminf).  R bounds every |coordinate - O| that
+// can occur on this path (edges lie in the bbox, p passed the x-range test and t < nb + 1 puts p.y at most
+// one bucket above ymax: factor 2, absorbed below).  Each float difference u,v,w,z carries two conversions
+// and one subtraction, each <= 2^-24 relative: |u - U| <= 3 * 2^-24 * 2R < eta := 2^-20 R.
+//   ordinates  : |w| > eta and |v| > eta  =>  sign(w), sign(v) are the exact signs of (sy-py), (ey-py): the
+//                predicates a, b, c of edge_rule_fast are known exactly and sy != py, ey != py;
+//   determinant: |det - D| <= eta(|u|+|v|+|w|+|z| + 2 eta) + 2^-22(|uv|+|wz|)  (input perturbation plus
+//                three float roundings) <= eta * 8.5 R + 2^-19 R^2 =: B  because |u|,|v|,|w|,|z| <= 2R;
+//                so |det| > B  =>  sign(det) = sign(D) != 0.  B is one constant per (point, part).
+// Anything else raises `undecided`; the point is then recomputed from the f64 records with the exact
+// predicate.  A definite answer is therefore always geo's answer.
+__device__ __forceinline__ void fast_edge_rule(float4 e, float qx, float qy, float eta, float B, int &wn, bool &undecided) {
+    const float u = e.x - qx, w = e.y - qy, z = e.z - qx, v = e.w - qy;
+    const bool cert_y = fabsf(w) > eta && fabsf(v) > eta;
+    const bool wl = w < 0.0f, vl = v < 0.0f;
+    const bool act = wl != vl;
+    const float det = u * v - w * z;
+    undecided = undecided || !cert_y || (act && !(fabsf(det) > B));
+    wn += (int)(act && wl && det > 0.0f) - (int)(act && !wl && det < 0.0f);
+}
+__device__ __forceinline__ void ld256f(const float4 *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+// returns Polygon::contains for a plain part when `undecided` stays false
+__device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const PartLite &l, double px, double py, bool &undecided) {
+    if (!(px >= (double)l.xminf && px <= (double)l.xmaxf)) return false;
+    const int32_t nb = l.nb_flags & 0x00ffffff;
+    const int32_t C = ((l.nb_flags >> kFastCShift) & 63) * 2;
+    const float qx = __double2float_rn(px - (double)l.xminf), qy = __double2float_rn(py - (double)l.yminf);
+    const float tq = qy * l.inv_hf;
+    // qy < 0 <=> p.y < yminf <= ymin ; tq >= nb + 1 => p.y > ymax : no listed edge can act
+    if (qy < 0.0f || !(tq < (float)(nb + 1))) return false;
+    const int32_t b = min((int32_t)tq, nb - 1);
+    const float4 *rec = fast + (int64_t)l.bucket_base + (int64_t)b * C;
+    const float height = l.inv_hf > 0.0f ? (float)nb / l.inv_hf : 0.0f;
+    const float R = fmaxf(l.xmaxf - l.xminf, height);
+    const float eta = 9.5367431640625e-07f * R;                          // 2^-20 R
+    const float B = 1.01f * (8.5f * eta * R + 1.9073486328125e-06f * R * R);  // eta*8.5R + 2^-19 R^2
+    const float inf = __int_as_float(0x7f800000);
+    int wn = 0;
+    bool und = false;
+    // first batch: header + up to 7 edges (4 sectors), issued together; sentinels make the count irrelevant here
+    float4 r[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        r[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
+        r[2 * j + 1] = r[2 * j];
+        if (2 * j < C) ld256f(rec + 2 * j, r[2 * j], r[2 * j + 1]);
+    }
+    const int32_t count = __float_as_int(r[0].x);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
+    for (int32_t k = 8; k <= count; k += 8) {  // records 8.. (edge index k-1): only for lists longer than 7
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            r[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
+            r[2 * j + 1] = r[2 * j];
+            if (k + 2 * j <= count) ld256f(rec + k + 2 * j, r[2 * j], r[2 * j + 1]);  // slots past `count` are sentinels
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
+    }
+    undecided = undecided || und;
+    return wn != 0;
+}
+
 // MODE 0: first_id (+ optional count); undecided points get first_id = kDeferred and bump *n_deferred.
 // MODE 1: write every (point, polygon) pair at pair_off[i]; undecided candidates are resolved in place
 //         with the exact predicate (this mode is not the throughput path).
@@ -601,7 +754,8 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const
                                                                            const int64_t *__restrict__ pair_off,
                                                                            uint64_t *__restrict__ lhs, uint64_t *__restrict__ rhs,
                                                                            int64_t point_base,
-                                                                           unsigned long long *__restrict__ n_deferred) {
+                                                                           unsigned long long *__restrict__ n_deferred,
+                                                                           uint32_t *__restrict__ deferred_list, uint32_t list_cap) {
     const GridParams &g = ix.grid;
     const int64_t stride = (int64_t)gridDim.x * kQueryThreads;
     int64_t i = (int64_t)blockIdx.x * kQueryThreads + threadIdx.x;
@@ -626,6 +780,35 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const
                 PartLite lite;
                 if (c == 0 && !ix.multi) {
                     unpack_lite(r + 2, lite);
+                    if (lite.nb_flags & kFastBit) {  // single plain candidate: FP32 filter over the fast table
+                        bool und = false;
+                        bool inside = fast_walk(ix.fast, lite, p.x, p.y, und);
+                        if (und) {
+                            if (MODE == 0) {
+                                undecided = true;
+                                break;
+                            }
+                            // pair mode: resolve in place from the f64 records
+                            int32_t q[8];
+                            ld256(ix.parts + first_part, q);
+                            PartLite gl;
+                            unpack_lite(q, gl);
+                            int32_t a0, a1;
+                            inside = candidate_range(ix, gl, p.x, p.y, a0, a1) &&
+                                     bucket_contains_exact(ix.entries, ix.entry_ring, false, a0, a1, p.x, p.y);
+                        }
+                        if (inside) {
+                            if (MODE == 1) {
+                                lhs[w] = (uint64_t)(point_base + i);
+                                rhs[w] = (uint64_t)first_part;
+                                ++w;
+                            } else {
+                                first = first_part;
+                                cnt = 1;
+                            }
+                        }
+                        break;
+                    }
                     if (n_cand > 1) part = __ldg(ix.cell_items + first_part);
                     geom = part;
                 } else {
@@ -664,7 +847,8 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const
         if (MODE == 0) {
             if (undecided) {
                 first = kDeferred;
-                atomicAdd(n_deferred, 1ULL);
+                const unsigned long long slot = atomicAdd(n_deferred, 1ULL);
+                if (slot < list_cap) deferred_list[slot] = (uint32_t)i;  // chunk-relative index (chunks are < 2^32 points)
             }
             __stcs(first_id + i, first);
             if (count) __stcs(count + i, cnt);
@@ -672,36 +856,47 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const
     }
 }
 
-// Exact re-evaluation of the points k_pip_query<0> marked kDeferred (those whose orientation filter
-// failed on an edge that mattered: collinear or within a few ulps of an edge).  Launched after every
-// query; exits immediately when the counter is zero.
+// Exact re-evaluation of the points k_pip_query<0> marked kDeferred (those whose filters could not
+// certify an ordinate relation or an orientation that mattered: points within ~1e-6 of an edge or of a
+// vertex ordinate, relative to the part size).  Launched after every query; exits at once when the
+// counter is zero.  One thread per deferred point, taken from the list the query kernel appended to; if
+// the list overflowed, the id column is scanned for the marker instead.
+__device__ __forceinline__ void deferred_point(const IndexView &ix, const double2 *__restrict__ pts, int64_t i,
+                                               int32_t *__restrict__ first_id, int32_t *__restrict__ count) {
+    const GridParams &g = ix.grid;
+    const double2 p = pts[i];
+    const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
+    const CellRec cell = ix.cells[(int64_t)cy * g.gx + cx];
+    int32_t first = -1, cnt = 0, last_geom = -1;
+    for (int32_t c = 0; c < cell.count; ++c) {
+        const int32_t part = cell.count == 1 ? cell.first : ix.cell_items[cell.first + c];
+        const PartRec rec = ix.parts[part];
+        if (rec.geom == last_geom) continue;
+        int32_t e0, e1;
+        if (!candidate_range(ix, rec.lite, p.x, p.y, e0, e1)) continue;
+        if (!bucket_contains_exact(ix.entries, ix.entry_ring, rec.lite.nb_flags < 0, e0, e1, p.x, p.y)) continue;
+        last_geom = rec.geom;
+        if (first < 0) first = rec.geom;
+        ++cnt;
+        if (count == nullptr) break;
+    }
+    first_id[i] = first;
+    if (count) count[i] = cnt;
+}
 __global__ void __launch_bounds__(256) k_pip_deferred(const IndexView ix, const double2 *__restrict__ pts, int64_t n_pts,
                                                       int32_t *__restrict__ first_id, int32_t *__restrict__ count,
-                                                      const unsigned long long *__restrict__ n_deferred) {
-    if (*n_deferred == 0ULL) return;
-    const GridParams &g = ix.grid;
+                                                      const unsigned long long *__restrict__ n_deferred,
+                                                      const uint32_t *__restrict__ deferred_list, uint32_t list_cap) {
+    const unsigned long long nd = *n_deferred;
+    if (nd == 0ULL) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
-        if (first_id[i] != kDeferred) continue;
-        const double2 p = pts[i];
-        const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
-        const CellRec cell = ix.cells[(int64_t)cy * g.gx + cx];
-        int32_t first = -1, cnt = 0, last_geom = -1;
-        for (int32_t c = 0; c < cell.count; ++c) {
-            const int32_t part = cell.count == 1 ? cell.first : ix.cell_items[cell.first + c];
-            const PartRec rec = ix.parts[part];
-            if (rec.geom == last_geom) continue;
-            int32_t e0, e1;
-            if (!candidate_range(ix, rec.lite, p.x, p.y, e0, e1)) continue;
-            if (!bucket_contains_exact(ix.entries, ix.entry_ring, rec.lite.nb_flags < 0, e0, e1, p.x, p.y)) continue;
-            last_geom = rec.geom;
-            if (first < 0) first = rec.geom;
-            ++cnt;
-            if (count == nullptr) break;
-        }
-        first_id[i] = first;
-        if (count) count[i] = cnt;
+    if (nd <= list_cap) {
+        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)nd; k += stride)
+            deferred_point(ix, pts, (int64_t)deferred_list[k], first_id, count);
+        return;
     }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride)
+        if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count);
 }
 
 __global__ void k_histogram(const int32_t *__restrict__ ids, int64_t n, unsigned long long *__restrict__ counts,
@@ -717,26 +912,49 @@ static IndexView view_of(const gpl_pip_index *idx) {
     IndexView v;
     v.cells = idx->cells, v.cell_items = idx->cell_overflow, v.parts = idx->parts;
     v.bucket_range = idx->bucket_range, v.entries = idx->entries, v.entry_ring = idx->entry_ring;
+    v.fast = idx->fast;
     v.multi = idx->multi ? 1 : 0;
     v.grid = idx->grid;
     return v;
 }
 
 static int query_grid(int64_t n) {
-    // persistent-style: 148 SMs x 8 resident CTAs of 256 threads, grid-stride over the point stream
-    int64_t want = ceil_div(n, 256);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * 8));
+    // persistent-style: 148 SMs x resident CTAs, grid-stride over the point stream
+    static const int per_sm = []() {
+        const char *e = getenv("GPL_PIP_CTAS_PER_SM");
+        return e ? atoi(e) : 8;
+    }();
+    int64_t want = ceil_div(n, kQueryThreads);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
 
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
               int32_t *first_dev, int32_t *count_dev, cudaStream_t stream) {
     if (n == 0) return GPL_OK;
     const double2 *pts = reinterpret_cast<const double2 *>(pts_dev);
-    GPL_CUDA(cudaMemsetAsync(idx->n_deferred, 0, sizeof(unsigned long long), stream));
-    k_pip_query<0><<<query_grid(n), kQueryThreads, 0, stream>>>(view_of(idx), pts, validity_dev, n, first_dev, count_dev, nullptr,
-                                                                  nullptr, nullptr, 0, idx->n_deferred);
-    k_pip_deferred<<<kSMs * 4, 256, 0, stream>>>(view_of(idx), pts, n, first_dev, count_dev, idx->n_deferred);
-    ctx->launches += 2;
+    const IndexView v = view_of(idx);
+    // the deferred list holds chunk-relative uint32 indices: process at most 2^31 points per launch pair
+    const int64_t kMaxChunk = 1LL << 31;
+    for (int64_t lo = 0; lo < n; lo += kMaxChunk) {
+        const int64_t m = std::min(kMaxChunk, n - lo);
+        const uint32_t cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(m / 16, 1 << 16), 1 << 26);
+        if (idx->deferred_cap < cap) {
+            gpl_pip_index *mut = const_cast<gpl_pip_index *>(idx);
+            ctx->release(mut->deferred_list);
+            void *q = nullptr;
+            GPL_TRY(ctx->alloc(sizeof(uint32_t) * (size_t)cap, &q));
+            mut->deferred_list = (uint32_t *)q;
+            mut->deferred_cap = cap;
+        }
+        GPL_CUDA(cudaMemsetAsync(idx->n_deferred, 0, sizeof(unsigned long long), stream));
+        k_pip_query<0><<<query_grid(m), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr, m,
+                                                                      first_dev + lo, count_dev ? count_dev + lo : nullptr, nullptr,
+                                                                      nullptr, nullptr, lo, idx->n_deferred, idx->deferred_list,
+                                                                      idx->deferred_cap);
+        k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
+                                                     idx->n_deferred, idx->deferred_list, idx->deferred_cap);
+        ctx->launches += 2;
+    }
     GPL_CUDA(cudaGetLastError());
     return GPL_OK;
 }
@@ -758,9 +976,10 @@ static void l2_pin(gpl_pip_index *idx, bool on) {
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
     if (on) {
-        size_t carve = std::min<size_t>(idx->slab_bytes, ctx->l2_persist_max);
+        const size_t want = idx->hot_bytes ? idx->hot_bytes : idx->slab_bytes;
+        size_t carve = std::min<size_t>(want, ctx->l2_persist_max);
         (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-        size_t win = std::min<size_t>(idx->slab_bytes, ctx->l2_window_max);
+        size_t win = std::min<size_t>(want, ctx->l2_window_max);
         attr.accessPolicyWindow.base_ptr = idx->slab;
         attr.accessPolicyWindow.num_bytes = win;
         attr.accessPolicyWindow.hitRatio = win > 0 ? std::min(1.0f, (float)carve / (float)win) : 0.0f;
@@ -782,6 +1001,7 @@ extern "C" void gpl_pip_index_free(gpl_pip_index *idx) {
     if (!idx) return;
     if (idx->slab) l2_pin(idx, false);
     idx->ctx->release(idx->slab);
+    idx->ctx->release(idx->deferred_list);
     delete idx;
 }
 extern "C" int64_t gpl_pip_index_bytes(const gpl_pip_index *idx) { return idx ? idx->bytes : 0; }
@@ -821,13 +1041,13 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     // ---- phase 1 (scratch): bboxes, grid, cell counts, bucket counts --------------------------------
     Scratch<PartHeader> hdr;
     Scratch<GridParams> gp;
-    Scratch<int32_t> parent, nb, base, cell_count, cell_start, bcount, bstart;
+    Scratch<int32_t> parent, nb, base, cell_count, cell_start, bcount, bstart, fast_c, fast_slots, fast_base;
     Scratch<int64_t> totals;
     TRYF(hdr.get(ctx, (size_t)Pa));
     TRYF(gp.get(ctx, 1));
     TRYF(nb.get(ctx, (size_t)Pa + 1));
     TRYF(base.get(ctx, (size_t)Pa + 1));
-    TRYF(totals.get(ctx, 4));
+    TRYF(totals.get(ctx, 8));
     const int32_t *parent_p = nullptr;
     if (type == GPL_MULTIPOLYGON) {
         TRYF(parent.get(ctx, (size_t)Pa));
@@ -875,16 +1095,26 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         ctx->launches++;
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, bcount.p, NB_cap, bstart.p, totals.p + 2)));
+    // FP32 fast table plan: records per bucket (C) of every eligible part, then their bases
+    TRYF(fast_c.get(ctx, (size_t)Pa + 1));
+    TRYF(fast_slots.get(ctx, (size_t)Pa + 1));
+    TRYF(fast_base.get(ctx, (size_t)Pa + 1));
+    if (P > 0) {
+        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, fast_c.p, fast_slots.p);
+        ctx->launches++;
+    }
+    TRYF((exclusive_scan<int32_t, int32_t>(ctx, fast_slots.p, P, fast_base.p, totals.p + 3)));
 
     // the data-dependent sizes + the grid parameters: one small D2H (index build is once per join)
-    int64_t h_tot[3];
-    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, st));
+    int64_t h_tot[4];
+    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 4, cudaMemcpyDeviceToHost, st));
     CUDAF(cudaMemcpyAsync(&idx->grid, gp.p, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
     CUDAF(cudaStreamSynchronize(st));
     idx->n_overflow = h_tot[0];  // all cell items
     idx->n_buckets = h_tot[1];
     idx->n_entries = h_tot[2];
-    if (idx->n_entries >= (1LL << 31) || idx->n_overflow >= (1LL << 31)) {
+    idx->n_fast = h_tot[3];
+    if (idx->n_fast >= (1LL << 31) || idx->n_entries >= (1LL << 31) || idx->n_overflow >= (1LL << 31)) {
         set_error("join index too large (%lld edge records, %lld cell items)", (long long)idx->n_entries,
                   (long long)idx->n_overflow);
         return fail(GPL_ERR_UNSUPPORTED);
@@ -899,13 +1129,19 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         off = align_up(off + bytes, 256);
         return o;
     };
+    // hot structures first: the L2-persisting window covers [0, hot_bytes) only, so the f64 records that
+    // just the exact kernel reads do not compete for the cache with the tables every point touches
     const size_t o_cells = carve(sizeof(CellRec) * n_cells);
+    const size_t o_fast = carve(sizeof(float4) * (idx->n_fast + 8));
     const size_t o_parts = carve(sizeof(PartRec) * Pa);
     const size_t o_brange = carve(sizeof(int2) * (idx->n_buckets + 1));
-    const size_t o_entries = carve(sizeof(EdgeRec) * (idx->n_entries + 1));
     const size_t o_items = carve(sizeof(int32_t) * (idx->n_overflow + 1));
-    const size_t o_ring = idx->any_holes ? carve(sizeof(int32_t) * (idx->n_entries + 1)) : 0;
     const size_t o_defer = carve(sizeof(unsigned long long));
+    const bool all_fast = idx->n_fast > 0 && !idx->multi && !idx->any_holes;
+    const size_t hot_mark = off;
+    const size_t o_entries = carve(sizeof(EdgeRec) * (idx->n_entries + 1));
+    const size_t o_ring = idx->any_holes ? carve(sizeof(int32_t) * (idx->n_entries + 1)) : 0;
+    idx->hot_bytes = all_fast ? hot_mark : 0;  // 0: pin the whole slab (general-path parts read the f64 records)
     void *q = nullptr;
     TRYF(ctx->alloc(off, &q));
     idx->slab = (uint8_t *)q;
@@ -917,6 +1153,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     idx->cell_overflow = (int32_t *)(idx->slab + o_items);
     idx->entry_ring = idx->any_holes ? (int32_t *)(idx->slab + o_ring) : nullptr;
     idx->n_deferred = (unsigned long long *)(idx->slab + o_defer);
+    idx->fast = (float4 *)(idx->slab + o_fast);
     idx->bytes = (int64_t)off;
 
     Scratch<int64_t> entry_edge;
@@ -926,7 +1163,8 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         k_cells<1><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, idx->cell_overflow);
         ctx->launches++;
     }
-    k_cell_finish<<<(int)ceil_div(n_cells, 128), 128, 0, st>>>(idx->cells, cell_start.p, idx->cell_overflow, hdr.p, n_cells);
+    k_cell_finish<<<(int)ceil_div(n_cells, 128), 128, 0, st>>>(idx->cells, cell_start.p, idx->cell_overflow, hdr.p, fast_c.p, fast_base.p,
+                                                                n_cells);
     ctx->launches++;
     if (idx->n_buckets > 0) {
         k_bucket_ranges<<<(int)ceil_div(idx->n_buckets, 256), 256, 0, st>>>(bstart.p, idx->bucket_range, idx->n_buckets);
@@ -941,6 +1179,10 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         k_sort_segments<int64_t><<<(int)ceil_div(nbk, 128), 128, 0, st>>>(entry_edge.p, bstart.p, idx->n_buckets);
         k_materialise<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bstart.p,
                                              entry_edge.p, idx->entries, idx->entry_ring);
+        if (idx->n_fast > 0) {
+            k_fast_fill<<<wgrid, 256, 0, st>>>(hdr.p, P, fast_c.p, fast_base.p, bstart.p, idx->entries, idx->fast);
+            ctx->launches++;
+        }
         ctx->launches += 4;
         CUDAF(cudaGetLastError());
     }
@@ -1032,7 +1274,7 @@ extern "C" int gpl_contains_join_pairs(gpl_ctx *ctx, const gpl_pip_index *idx, c
         pl = dl.p, pr = dr.p;
     }
     k_pip_query<1><<<query_grid(n_points), kQueryThreads, 0, ctx->stream>>>(view_of(idx), reinterpret_cast<const double2 *>(pdev), nullptr,
-                                                                      n_points, nullptr, nullptr, off.p, pl, pr, 0, nullptr);
+                                                                      n_points, nullptr, nullptr, off.p, pl, pr, 0, nullptr, nullptr, 0);
     ctx->launches++;
     GPL_CUDA(cudaGetLastError());
     if (mem == GPL_HOST) {
