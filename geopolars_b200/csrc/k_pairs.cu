@@ -7,14 +7,20 @@
 //
 // Design: one warp per row.  Both linestrings of the row are staged into shared memory with one
 // coalesced LDG.128 per lane (BASELINE config 3: 16+16 coords = 512 B per row, one warp-wide load), then
-//   intersects: lanes stride over the (na-1)*(nb-1) segment pairs; closed bbox reject (exact) before
-//               the 2-4 exact orient2d calls; warp-wide early exit with __any_sync;
+//   intersects: per-segment bounding boxes once; lanes stride over the (na-1)*(nb-1) segment pairs doing only
+//               the closed-bbox reject (exact), survivors are compacted with __ballot_sync into a small
+//               shared-memory queue and tested 32 at a time by a BRANCH-FREE rule: four orientation
+//               determinants with Shewchuk's stage-A filter; four certified non-zero signs decide the pair
+//               exactly like geo's Line x Line rule, anything else (collinear, degenerate, within rounding)
+//               marks the row and — only if no certified hit exists — the whole row is redone with the
+//               exact adaptive predicate (warp-uniform call, rare).  Early exit with __any_sync.
 //   distance  : only if not intersecting; lanes stride over the nb*(na-1) + na*(nb-1) (vertex, segment)
-//               items, keep min SQUARED distance (no hypot/division on the endpoint cases, one division
-//               on interior projections), one sqrt after the warp min.  The cancellation-prone term
-//               (the cross product) is evaluated with exactly the reference's expression, so the result
-//               differs from geo's |s|*hypot(dx,dy) only by the last two roundings (<= 4 ulp; the stated
-//               tolerance for f64 outputs is 1e-9 relative).
+//               items, branch-free: the three candidate squared distances are formed and the minimum is
+//               tracked as a FRACTION (numerator, denominator) compared by cross-multiplication, one
+//               division + one sqrt per row.  The cancellation-prone term (the cross product) uses
+//               exactly the reference's expression, so the result differs from geo's |s|*hypot(dx,dy) only
+//               by the last roundings (<= 4 ulp; the stated tolerance for f64 outputs is 1e-9 relative).
+// Rows longer than 33 coordinates per side use the straightforward generic path below.
 // These kernels are FP64-ALU bound, not HBM bound (~225 segment tests + ~480 distance items per 512 B).
 #include <math.h>
 
@@ -119,6 +125,118 @@ __device__ __forceinline__ double ls_ls_min_dist2(Coords A, int64_t na, Coords B
     return warp_min(best);
 }
 
+// ---- fast paths for short linestrings (<= 33 coords per side, staged in shared memory) ----------------
+constexpr int kPairQueue = 64;
+
+// sign of orient2d(a,b,c) when the stage-A filter certifies it (non-zero), else 0 and `unsure` is raised
+__device__ __forceinline__ int certified_sign(double2 a, double2 b, double2 c, bool &unsure) {
+    const double dl = (a.x - c.x) * (b.y - c.y);
+    const double dr = (a.y - c.y) * (b.x - c.x);
+    const double det = dl - dr;
+    const bool certain = fabs(det) > kCcwA * (fabs(dl) + fabs(dr));
+    unsure = unsure || !certain;
+    return certain ? ((det > 0.0) ? 1 : -1) : 0;
+}
+
+// intersects for na, nb <= 33.  A, B: the row's coordinates in SHARED memory; box: per-warp scratch of 64
+// float4 (conservative float bounding boxes of A's and B's segments: min rounded down, max rounded up — a
+// looser box only adds candidates); queue: per-warp scratch of kPairQueue ushorts.  Warp-uniform result:
+// 0 / 1 = geo's answer (has_disjoint_bboxes of the whole linestrings is implied: disjoint boxes give no
+// candidate), 2 = undecided by the filter: the row goes to k_ls_ls_exact.
+__device__ __forceinline__ int ls_intersects_ls_short(const double2 *A, int32_t na, const double2 *B, int32_t nb, float4 *box,
+                                                      unsigned short *queue, int lane) {
+    if (na < 2 || nb < 2) return 0;
+    const int32_t sa = na - 1, sb = nb - 1;
+    if (lane < sa) {
+        const double2 p = A[lane], q = A[lane + 1];
+        box[lane] = make_float4(__double2float_rd(fmin(p.x, q.x)), __double2float_rd(fmin(p.y, q.y)), __double2float_ru(fmax(p.x, q.x)),
+                                __double2float_ru(fmax(p.y, q.y)));
+    }
+    if (lane < sb) {
+        const double2 p = B[lane], q = B[lane + 1];
+        box[32 + lane] = make_float4(__double2float_rd(fmin(p.x, q.x)), __double2float_rd(fmin(p.y, q.y)),
+                                     __double2float_ru(fmax(p.x, q.x)), __double2float_ru(fmax(p.y, q.y)));
+    }
+    __syncwarp();
+    const int32_t total = sa * sb;
+    // (i, j) of this lane's segment pair, advanced by 32 pairs per step without dividing
+    int32_t i = lane / sb, j = lane - i * sb;
+    const int32_t di = 32 / sb, dj = 32 - di * sb;
+    int32_t qn = 0;
+    bool unsure_any = false;
+    for (int32_t base = 0; base < total || qn > 0; base += 32) {
+        // 1. bbox filter of 32 segment pairs, survivors appended to the queue
+        bool cand = false;
+        if (base + lane < total) {
+            const float4 x = box[i], y = box[32 + j];
+            cand = !(x.z < y.x || y.z < x.x || x.w < y.y || y.w < x.y);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)((i << 8) | j);
+        qn += __popc(m);
+        i += di, j += dj;
+        if (j >= sb) j -= sb, ++i;
+        __syncwarp();
+        // 2. dense exact-sign test of up to 32 queued candidates (when a full batch is available, or at the end)
+        if (qn >= 32 || (base + 32 >= total && qn > 0)) {
+            const int32_t take = min(qn, 32);
+            bool hit = false, unsure = false;
+            if (lane < take) {
+                const unsigned short c = queue[qn - take + lane];
+                const int32_t ci = c >> 8, cj = c & 0xff;
+                const double2 a0 = A[ci], a1 = A[ci + 1], b0 = B[cj], b1 = B[cj + 1];
+                // geo: self = (b0,b1), rhs = (a0,a1)
+                const int c11 = certified_sign(b0, b1, a0, unsure), c12 = certified_sign(b0, b1, a1, unsure);
+                const int c21 = certified_sign(a0, a1, b0, unsure), c22 = certified_sign(a0, a1, b1, unsure);
+                hit = !unsure && c11 != c12 && c21 != c22;
+                // certified c11 == c12 (both non-zero) means "no intersection" whatever c21/c22 are
+                if (c11 != 0 && c11 == c12) unsure = false;
+            }
+            if (__any_sync(0xffffffffu, hit)) return 1;
+            unsure_any = unsure_any || __any_sync(0xffffffffu, unsure);
+            qn -= take;
+            __syncwarp();
+        }
+    }
+    return unsure_any ? 2 : 0;  // 2: some candidate was collinear / degenerate / too close to call and nothing certified
+}
+
+// min distance for na, nb <= 33, not intersecting: fraction-tracked squared distance, branch-free
+__device__ __forceinline__ double ls_ls_distance_short(const double2 *A, int32_t na, const double2 *B, int32_t nb, int lane) {
+    const int32_t sa = na - 1, sb = nb - 1;
+    double best_n = 1.7976931348623157e308, best_d = 1.0;
+    // two sweeps with the same body: vertices of P against segments of S
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        const double2 *P = sweep == 0 ? B : A, *S = sweep == 0 ? A : B;
+        const int32_t np = sweep == 0 ? nb : na, ns = sweep == 0 ? sa : sb;
+        const int32_t total = np * ns;
+        int32_t pi = lane / ns, si = lane - pi * ns;
+        const int32_t dp = 32 / ns, ds = 32 - dp * ns;
+        for (int32_t t = lane; t < total; t += 32) {
+            const double2 p = P[pi], s = S[si], e = S[si + 1];
+            const double dx = e.x - s.x, dy = e.y - s.y;
+            const double wx = p.x - s.x, wy = p.y - s.y;
+            const double ux = p.x - e.x, uy = p.y - e.y;
+            const double dd = dx * dx + dy * dy;
+            const double num = wx * dx + wy * dy;
+            const double ww = wx * wx + wy * wy, uu = ux * ux + uy * uy;
+            const double cross = (s.y - p.y) * dx - (s.x - p.x) * dy;  // the reference's expression
+            const bool interior = num > 0.0 && num < dd;               // 0 < r < 1 (exact: see seg_dist2)
+            const double n = interior ? cross * cross : ((num <= 0.0 || dd == 0.0) ? ww : uu);
+            const double d = interior ? dd : 1.0;
+            if (n * best_d < best_n * d) {
+                best_n = n;
+                best_d = d;
+            }
+            pi += dp, si += ds;
+            if (si >= ns) si -= ns, ++pi;
+        }
+    }
+    double v = best_n / best_d;
+    v = warp_min(v);
+    return sqrt(v);
+}
+
 // stage a row's coordinates in shared memory when they fit, else hand back the global pointer
 __device__ __forceinline__ Coords stage(const double2 *__restrict__ g, int64_t c0, int64_t n, double2 *smem, bool fits, int lane) {
     if (!fits) return Coords{g + c0};
@@ -127,40 +245,120 @@ __device__ __forceinline__ Coords stage(const double2 *__restrict__ g, int64_t c
 }
 
 // MODE 0: intersects -> byte per row   MODE 1: distance -> f64 (+ validity byte)
+//
+// Fast kernel: rows with <= 33 coordinates per side.  No calls, no adaptive-precision code (64-ish
+// registers instead of 108); the next row's coordinates are prefetched into registers while the current
+// row is processed.  Rows it cannot finish — longer linestrings, or a filter that could not certify a
+// sign that mattered — get flag[r] = 1 and are redone by k_ls_ls_exact.
 template <int MODE>
-__global__ void __launch_bounds__(kPairWarps * 32) k_ls_ls(int64_t n, const double2 *__restrict__ axy,
-                                                           const int64_t *__restrict__ aoff, const uint8_t *__restrict__ avalid,
-                                                           const double2 *__restrict__ bxy, const int64_t *__restrict__ boff,
-                                                           const uint8_t *__restrict__ bvalid, uint8_t *__restrict__ out_bool,
-                                                           double *__restrict__ out_dist, uint8_t *__restrict__ out_valid) {
-    __shared__ double2 smem[kPairWarps][kPairSmemCoords];
+__global__ void __launch_bounds__(kPairWarps * 32, 3) k_ls_ls_fast(int64_t n, const double2 *__restrict__ axy,
+                                                                   const int64_t *__restrict__ aoff, const uint8_t *__restrict__ avalid,
+                                                                   const double2 *__restrict__ bxy, const int64_t *__restrict__ boff,
+                                                                   const uint8_t *__restrict__ bvalid, uint8_t *__restrict__ out_bool,
+                                                                   double *__restrict__ out_dist, uint8_t *__restrict__ out_valid,
+                                                                   uint8_t *__restrict__ flag) {
+    __shared__ double2 smem[kPairWarps][68];
+    __shared__ float4 s_box[kPairWarps][64];
+    __shared__ unsigned short s_queue[kPairWarps][kPairQueue];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int64_t warp = (int64_t)blockIdx.x * kPairWarps + wid;
+    double2 *sm = smem[wid];
     const int64_t nwarps = (int64_t)gridDim.x * kPairWarps;
-    for (int64_t r = warp; r < n; r += nwarps) {
-        bool valid = bit_get(avalid, r) && bit_get(bvalid, r);
-        int64_t a0 = aoff[r], na = aoff[r + 1] - a0, b0 = boff[r], nb = boff[r + 1] - b0;
-        bool fits = na + nb <= kPairSmemCoords;
+    int64_t r = (int64_t)blockIdx.x * kPairWarps + wid;
+    // prefetch registers: lane holds coords lane, lane+32, lane+64 of the concatenation A ++ B of the next row
+    double2 pf[3];
+    int64_t a0 = 0, b0 = 0;
+    int32_t na = 0, nb = 0;
+    bool shortp = false;
+    auto fetch = [&](int64_t row) {
+        a0 = aoff[row], b0 = boff[row];
+        const int64_t la = aoff[row + 1] - a0, lb = boff[row + 1] - b0;
+        shortp = la <= 33 && lb <= 33;
+        na = (int32_t)min(la, (int64_t)34), nb = (int32_t)min(lb, (int64_t)34);
+        if (shortp) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int32_t c = lane + 32 * k;
+                if (c < na) pf[k] = __ldcs(axy + a0 + c);
+                else if (c < na + nb) pf[k] = __ldcs(bxy + b0 + (c - na));
+            }
+        }
+    };
+    if (r < n) fetch(r);
+    for (; r < n; r += nwarps) {
+        const bool valid = bit_get(avalid, r) && bit_get(bvalid, r);
+        const bool cur_short = shortp;
+        const int32_t cna = na, cnb = nb;
         __syncwarp();
-        Coords A = stage(axy, a0, na, smem[wid], fits, lane);
-        Coords B = stage(bxy, b0, nb, smem[wid] + (fits ? na : 0), fits, lane);
+        if (cur_short) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int32_t c = lane + 32 * k;
+                if (c < cna + cnb) sm[c] = pf[k];
+            }
+        }
+        if (r + nwarps < n) fetch(r + nwarps);  // overlaps the HBM latency of the next row with this row's math
         __syncwarp();
-        bool isect = valid && ls_intersects_ls(A, na, B, nb, lane);
+        int isect = 0;
+        if (valid && cur_short) isect = ls_intersects_ls_short(sm, cna, sm + cna, cnb, s_box[wid], s_queue[wid], lane);
+        const bool defer = valid && (!cur_short || isect == 2);
+        if (lane == 0) flag[r] = defer ? 1 : 0;
+        if (defer) continue;
         if (MODE == 0) {
-            if (lane == 0) out_bool[r] = isect ? 1 : 0;
+            if (lane == 0) out_bool[r] = isect == 1 ? 1 : 0;
         } else {
             double d = 0.0;
             bool ok = valid;
-            if (valid && !isect) {
-                if (na < 2 || nb < 2) {
-                    ok = false;  // reference: nearest_neighbor(..).unwrap() on an empty r-tree panics -> null
-                } else {
-                    d = sqrt(ls_ls_min_dist2(A, na, B, nb, lane));
-                }
+            if (valid && isect == 0) {
+                if (cna < 2 || cnb < 2) ok = false;  // reference: nearest_neighbor(..).unwrap() on an empty r-tree panics -> null
+                else d = ls_ls_distance_short(sm, cna, sm + cna, cnb, lane);
             }
             if (lane == 0) {
                 out_dist[r] = ok ? d : nan("");
                 if (out_valid) out_valid[r] = ok ? 1 : 0;
+            }
+        }
+    }
+}
+
+// Exact/generic kernel: redoes the rows k_ls_ls_fast flagged (any length, adaptive exact predicate).
+// Each warp scans 32 flags at a time and processes the flagged rows one after the other.
+template <int MODE>
+__global__ void __launch_bounds__(kPairWarps * 32) k_ls_ls_exact(int64_t n, const double2 *__restrict__ axy,
+                                                                 const int64_t *__restrict__ aoff, const double2 *__restrict__ bxy,
+                                                                 const int64_t *__restrict__ boff, const uint8_t *__restrict__ flag,
+                                                                 uint8_t *__restrict__ out_bool, double *__restrict__ out_dist,
+                                                                 uint8_t *__restrict__ out_valid) {
+    __shared__ double2 smem[kPairWarps][kPairSmemCoords];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * kPairWarps;
+    const int64_t n_blocks = (n + 31) >> 5;
+    for (int64_t blk = (int64_t)blockIdx.x * kPairWarps + wid; blk < n_blocks; blk += nwarps) {
+        const int64_t row0 = blk << 5;
+        unsigned todo = __ballot_sync(0xffffffffu, row0 + lane < n && flag[row0 + lane] != 0);
+        while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = row0 + bit;
+            const int64_t a0 = aoff[r], na = aoff[r + 1] - a0, b0 = boff[r], nb = boff[r + 1] - b0;
+            const bool fits = na + nb <= kPairSmemCoords;
+            __syncwarp();
+            Coords A = stage(axy, a0, na, smem[wid], fits, lane);
+            Coords B = stage(bxy, b0, nb, smem[wid] + (fits ? na : 0), fits, lane);
+            __syncwarp();
+            const bool isect = ls_intersects_ls(A, na, B, nb, lane);
+            if (MODE == 0) {
+                if (lane == 0) out_bool[r] = isect ? 1 : 0;
+            } else {
+                double d = 0.0;
+                bool ok = true;
+                if (!isect) {
+                    if (na < 2 || nb < 2) ok = false;
+                    else d = sqrt(ls_ls_min_dist2(A, na, B, nb, lane));
+                }
+                if (lane == 0) {
+                    out_dist[r] = ok ? d : nan("");
+                    if (out_valid) out_valid[r] = ok ? 1 : 0;
+                }
             }
         }
     }
@@ -401,11 +599,14 @@ extern "C" int gpl_intersects(gpl_ctx *ctx, const gpl_array *a, const gpl_array 
     GPL_CUDA(cudaSetDevice(ctx->device));
     int64_t n = a->n_geoms;
     if (n == 0) return GPL_OK;
-    Scratch<uint8_t> bytes;
+    Scratch<uint8_t> bytes, flag;
     GPL_TRY(bytes.get(ctx, (size_t)n));
-    GPL_LAUNCH(ctx, k_ls_ls<0>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, reinterpret_cast<const double2 *>(a->xy),
-               a->geom_off, a->validity, reinterpret_cast<const double2 *>(b->xy), b->geom_off, b->validity, bytes.p, nullptr,
-               nullptr);
+    GPL_TRY(flag.get(ctx, (size_t)n));
+    const double2 *axy = reinterpret_cast<const double2 *>(a->xy), *bxy = reinterpret_cast<const double2 *>(b->xy);
+    GPL_LAUNCH(ctx, k_ls_ls_fast<0>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,
+               b->validity, bytes.p, nullptr, nullptr, flag.p);
+    GPL_LAUNCH(ctx, k_ls_ls_exact<0>, warp_grid(ceil_div(n, 32), kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, bxy, b->geom_off,
+               flag.p, bytes.p, nullptr, nullptr);
     return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
 }
 
@@ -452,8 +653,12 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
     }
     const double2 *axy = reinterpret_cast<const double2 *>(a->xy), *bxy = reinterpret_cast<const double2 *>(b->xy);
     if (ta == GPL_LINESTRING && tb == GPL_LINESTRING) {
-        GPL_LAUNCH(ctx, k_ls_ls<1>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,
-                   b->validity, nullptr, dst, vb);
+        Scratch<uint8_t> flag;
+        GPL_TRY(flag.get(ctx, (size_t)n));
+        GPL_LAUNCH(ctx, k_ls_ls_fast<1>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,
+                   b->validity, nullptr, dst, vb, flag.p);
+        GPL_LAUNCH(ctx, k_ls_ls_exact<1>, warp_grid(ceil_div(n, 32), kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, bxy, b->geom_off,
+                   flag.p, nullptr, dst, vb);
     } else if (ta == GPL_POINT && tb == GPL_POINT) {
         GPL_LAUNCH(ctx, k_point_point_dist, (int)ceil_div(n, 256), 256, 0, n, axy, a->validity, bxy, b->validity, dst, vb);
     } else if (ta == GPL_POINT && tb == GPL_LINESTRING) {
