@@ -304,11 +304,28 @@ __global__ void __launch_bounds__(kHullWarps * 32) k_hull(int type, int64_t n_ge
                 if (!(em.first.x == pmin.x && em.first.y == pmin.y)) em.push(em.first, lane);  // LineString::close
             }
         }
-        if (!WRITE && lane == 0) counts[g] = em.n;
+        if (counts != nullptr && lane == 0) counts[g] = em.n;
         __syncwarp();
     }
 }
 
+// upper bound of the hull ring length of geometry g: all exterior coordinates + the closing vertex
+__global__ void k_hull_upper(int type, int64_t n_geoms, const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
+                             const int64_t *__restrict__ ring_off, int64_t *__restrict__ ub) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < n_geoms) ub[g] = exterior_count(type, g, geom_off, part_off, ring_off) + 2;
+}
+// one warp per geometry: move the ring from its slot in the temporary buffer to its final offset
+__global__ void __launch_bounds__(256) k_hull_compact(int64_t n_geoms, const double2 *__restrict__ tmp, const int64_t *__restrict__ tmp_off,
+                                                      const int64_t *__restrict__ out_off, double2 *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = warp; g < n_geoms; g += nwarps) {
+        const int64_t s = tmp_off[g], d = out_off[g], m = out_off[g + 1] - d;
+        for (int64_t k = lane; k < m; k += 32) out[d + k] = tmp[s + k];
+    }
+}
 __global__ void k_iota(int64_t *__restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
@@ -350,27 +367,60 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         GPL_TRY(workspace.get(ctx, per_warp * kHullWarps * (size_t)grid));
     }
     const size_t dyn = use_smem ? smem_bytes : 0;
-    if (n > 0) {
-        k_hull<false><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
-                                                                   cap, use_smem ? 1 : 0, workspace.p, counts.p, nullptr, nullptr);
-        ctx->launches++;
-        GPL_CUDA(cudaGetLastError());
-    }
     Scratch<int64_t> ring_off, geom_off;
     GPL_TRY(ring_off.get(ctx, (size_t)n + 1));
     GPL_TRY(geom_off.get(ctx, (size_t)n + 1));
-    GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
-    int64_t h_total = 0;
-    GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     Scratch<double> oxy;
-    GPL_TRY(oxy.get(ctx, (size_t)h_total * 2));
-    if (n > 0) {
+    int64_t h_total = 0;
+    // Single pass when a temporary of the upper-bound size fits (ring <= exterior coords + 2): the machine
+    // runs once, writes each ring into its slot and the rings are compacted afterwards.  Otherwise two
+    // passes (count, scan, re-run and write).
+    const size_t ub_coords = (size_t)in->n_coords + 2 * (size_t)n + 2;
+    // try to get the temporary from the context cache / the device; on OOM fall back to two passes
+    Scratch<double> tmp;
+    bool single = n > 0;
+    if (single && tmp.get(ctx, ub_coords * 2) != GPL_OK) {
+        single = false;
+        (void)cudaGetLastError();
+    }
+    if (single) {
+        Scratch<int64_t> ub, tmp_off;
+        GPL_TRY(ub.get(ctx, (size_t)n + 1));
+        GPL_TRY(tmp_off.get(ctx, (size_t)n + 1));
+        GPL_LAUNCH(ctx, k_hull_upper, (int)ceil_div(n, 256), 256, 0, in->type, n, in->geom_off, in->part_off, in->ring_off, ub.p);
+        GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, ub.p, n, tmp_off.p, nullptr)));
         k_hull<true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
-                                                                  cap, use_smem ? 1 : 0, workspace.p, nullptr, ring_off.p,
-                                                                  reinterpret_cast<double2 *>(oxy.p));
+                                                                  cap, use_smem ? 1 : 0, workspace.p, counts.p, tmp_off.p,
+                                                                  reinterpret_cast<double2 *>(tmp.p));
         ctx->launches++;
         GPL_CUDA(cudaGetLastError());
+        GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
+        GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        GPL_TRY(oxy.get(ctx, (size_t)h_total * 2));
+        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 8), (int64_t)kSMs * 8));
+        GPL_LAUNCH(ctx, k_hull_compact, cgrid, 256, 0, n, reinterpret_cast<const double2 *>(tmp.p), tmp_off.p, ring_off.p,
+                   reinterpret_cast<double2 *>(oxy.p));
+        GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp returns to the cache when this scope ends
+    } else {
+        if (n > 0) {
+            k_hull<false><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
+                                                                       in->validity, cap, use_smem ? 1 : 0, workspace.p, counts.p, nullptr,
+                                                                       nullptr);
+            ctx->launches++;
+            GPL_CUDA(cudaGetLastError());
+        }
+        GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
+        GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        GPL_TRY(oxy.get(ctx, (size_t)h_total * 2));
+        if (n > 0) {
+            k_hull<true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
+                                                                      in->validity, cap, use_smem ? 1 : 0, workspace.p, nullptr, ring_off.p,
+                                                                      reinterpret_cast<double2 *>(oxy.p));
+            ctx->launches++;
+            GPL_CUDA(cudaGetLastError());
+        }
     }
     // geom_off = identity: geometry i owns ring i (a null input row becomes an empty, null polygon)
     GPL_LAUNCH(ctx, k_iota, (int)ceil_div(n + 1, 256), 256, 0, geom_off.p, n + 1);

@@ -101,7 +101,9 @@ __device__ __forceinline__ void wc_add(WC &s, const WC &b) {
     }
 }
 // add_line_string over coords [c0,c1): 1-D sum of midpoint*len, 0-D sum of degenerate segment starts
-__device__ __forceinline__ WC line_string_wc(const double2 *__restrict__ xy, int64_t c0, int64_t c1, int lane) {
+// out of line: reached only by linestring rows and by degenerate (zero-area) rings; keeps the polygon hot
+// path of k_centroid at 64 registers
+static __device__ __noinline__ WC line_string_wc(const double2 *__restrict__ xy, int64_t c0, int64_t c1, int lane) {
     WC r{-1, 0.0, 0.0, 0.0};
     int64_t n = c1 - c0;
     if (n <= 0) return r;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void polygon_wc(WC &s, const double2 *xy, const int64
     }
 }
 
-__global__ void __launch_bounds__(256) k_centroid(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+__global__ void __launch_bounds__(256, 3) k_centroid(int type, int64_t n_geoms, const double2 *__restrict__ xy,
                                                   const int64_t *__restrict__ geom_off,
                                                   const int64_t *__restrict__ part_off,
                                                   const int64_t *__restrict__ ring_off,

@@ -110,3 +110,33 @@ def test_empty_inputs(ctx):
     xy, ro, go = synth.star_polygons(4, 2)
     idx2 = PipIndex(ctx.upload(GeoArrowArray.polygons(xy, ro, go)))
     assert idx2.query(np.zeros((0, 2))).shape == (0,)
+
+
+def test_large_rings_overlapping_boxes_and_deferred_overflow(ctx, og, conv):
+    """POLYGON rows that are not eligible for the FP32 fast table (buckets longer than 63 edges), cells with
+    several candidates (overlapping boxes), and a point set made almost entirely of boundary points so that
+    the deferred list overflows and the exact kernel falls back to scanning the id column."""
+    from geopolars_b200.engine import PipIndex
+
+    k = np.arange(3000)
+    th = 2 * np.pi * k / 3000
+    r = 10 + 3 * np.sin(40 * th)
+    big = np.stack([r * np.cos(th), r * np.sin(th)], 1)
+    big = np.concatenate([big, big[:1]])
+    sq = lambda x, y, s: [(x, y), (x + s, y), (x + s, y + s), (x, y + s), (x, y)]
+    shapes = [[big.tolist()], [sq(-3, -3, 6)], [sq(-1, -1, 9)], [sq(20, 20, 1)]]
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, shapes)
+    pts = np.concatenate([synth.uniform_points(150_000, scale=30.0) - 14.0, big[:-1], 0.5 * (big[:-1] + big[1:])])
+    want_first, want_cnt = og.contains_join(conv(polys), pts, use_grid=True, threads=0)
+    idx = PipIndex(ctx.upload(polys))
+    first, cnt = idx.query(pts, with_count=True)
+    assert np.array_equal(first, want_first) and np.array_equal(cnt, want_cnt)
+    assert cnt.max() == 3
+    # every point on a boundary: all deferred (list capacity is max(n/16, 65536) -> overflow -> scan path)
+    xy, ro, go = synth.star_polygons(400, 20)
+    stars = GeoArrowArray.polygons(xy, ro, go)
+    t = np.linspace(0.0, 1.0, 41)[None, :, None]
+    on_edges = (xy[:-1, None, :] * (1 - t) + xy[1:, None, :] * t).reshape(-1, 2)[:1_200_000]
+    wf, wc = og.contains_join(conv(stars), on_edges, use_grid=True, threads=0)
+    f2, c2 = PipIndex(ctx.upload(stars)).query(on_edges, with_count=True)
+    assert np.array_equal(f2, wf) and np.array_equal(c2, wc)
