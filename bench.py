@@ -142,7 +142,7 @@ def cpu_baseline_sample(n_sample: int, threads: int = 0):
     return n_sample / dt, cores, dt, int((first >= 0).sum())
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     """--impl reference: the reference's CPU path (restated: oracle/geo_oracle.c, kind 'port') on host cores."""
     rank = _env_int("RANK", 0)
     if rank != 0:
@@ -169,11 +169,22 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "geometries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
 def main():
+    # exactly ONE line goes to the real stdout (the JSON); anything libraries print (e.g. NCCL's version
+    # banner when NCCL_DEBUG=VERSION) is sent to stderr instead
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        return _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -188,7 +199,7 @@ def main():
     args = ap.parse_args()
 
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -354,7 +365,7 @@ def main():
         v, cores, dt, _ = cpu_baseline_sample(args.cpu_sample)
         line["cpu_baseline"] = {"value": v, "unit": "geometries/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_sample} of {n} points x {N_POLYGONS} polygons in {dt:.2f} s, oracle/geo_oracle.c OpenMP (bbox grid + exact test)"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -10,18 +10,18 @@
 //   * output = (lhs_index, rhs_index) pairs (spatial_index.rs:139-157).
 //
 // B200 design.  The polygon side is small (10 MB) and lives in the 126 MB L2; the point side is a
-// 1.6 GB stream.  Random points make every index access a gather, and a gather costs one L1 wavefront
-// per distinct 128-byte line per load instruction (measured: the first thread-per-point version of this
-// kernel sat at 84 % l1tex throughput).  The layout and the kernel are built around that limit:
+// 1.6 GB stream.  Random points make every index access a gather; measurements showed the
+// kernel limited first by divergence, then by L1 wavefronts (one per lane per load instruction), then by the
+// number of 32-byte L2 sectors pulled per point, and finally by issue slots.  The layout and the kernel are
+// built around those limits:
 //   grid cell (arithmetic)  -> ONE 32-byte record = candidate count + the first candidate's x-range and
 //                              y-bucket parameters (one 256-bit load)
-//   y-bucket (arithmetic)   -> (start,end) of a short list of 32-byte edge records whose closed y-range
-//                              can contain p.y (one 64-bit load)
-//   edge records            -> the 32 lanes of a warp pool the edge lists of their 32 points and walk
-//                              the pooled list 32 records at a time (one 256-bit load per record,
-//                              neighbouring lanes read neighbouring records => ~3 edges per wavefront),
-//                              winding contributions go to the owning point through shared-memory
-//                              atomics.  No lane idles while another walks a long list.
+//   y-bucket (arithmetic)   -> plain parts: fixed-stride FP32 table, header + edges as 16-byte float records
+//                              (no lookup at all: four 256-bit loads fetch the header and seven edges);
+//                              other parts: (start,end) of a list of 32-byte f64 edge records (one 64-bit load)
+//   edge rule               -> branch-free; an FP32 filter with a rigorous error bound on the fast table, the
+//                              f64 determinant with Shewchuk's stage-A filter elsewhere; whatever a filter
+//                              cannot certify is appended to a list and recomputed exactly by a second kernel.
 // Exactness of the pruning: geo's loop only ever acts on an edge when p.y lies in the edge's closed
 // y-range.  Buckets are assigned with f(y) = clamp(floor((y - ymin) * inv_h)), a monotone
 // non-decreasing function of y in IEEE arithmetic (subtraction, multiplication by a positive constant,
@@ -899,12 +899,30 @@ __global__ void __launch_bounds__(256) k_pip_deferred(const IndexView ix, const 
         if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count);
 }
 
-__global__ void k_histogram(const int32_t *__restrict__ ids, int64_t n, unsigned long long *__restrict__ counts,
-                            int64_t n_polys) {
+// per-polygon hit counts (config 4's all-reduce input).  Counts are privatised per CTA in shared memory
+// (32-bit, up to kHistSmemBins bins) and flushed once: 36 M global atomics on 10 k addresses become 1184 x 10 k.
+constexpr int kHistSmemBins = 48 * 1024;
+__global__ void __launch_bounds__(512) k_histogram(const int32_t *__restrict__ ids, int64_t n, unsigned long long *__restrict__ counts,
+                                                   int64_t n_polys, int use_smem) {
+    extern __shared__ unsigned int s_bins[];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (use_smem) {
+        for (int64_t b = threadIdx.x; b < n_polys; b += blockDim.x) s_bins[b] = 0u;
+        __syncthreads();
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        int32_t id = ids[i];
-        if (id >= 0 && id < n_polys) atomicAdd(&counts[id], 1ULL);
+        const int32_t id = __ldcs(ids + i);
+        if (id >= 0 && id < n_polys) {
+            if (use_smem) atomicAdd(&s_bins[id], 1u);
+            else atomicAdd(&counts[id], 1ULL);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int64_t b = threadIdx.x; b < n_polys; b += blockDim.x) {
+            const unsigned int v = s_bins[b];
+            if (v) atomicAdd(&counts[b], (unsigned long long)v);
+        }
     }
 }
 
@@ -1354,7 +1372,13 @@ extern "C" int gpl_join_histogram(gpl_ctx *ctx, const int32_t *first_id, int64_t
     GPL_REQUIRE(mem == GPL_DEVICE, GPL_ERR_UNSUPPORTED, "gpl_join_histogram: device buffers only");
     GPL_CUDA(cudaSetDevice(ctx->device));
     if (n_points == 0) return GPL_OK;
-    GPL_LAUNCH(ctx, k_histogram, query_grid(n_points), 256, 0, first_id, n_points, reinterpret_cast<unsigned long long *>(counts),
-               n_polygons);
+    const bool use_smem = n_polygons <= kHistSmemBins;
+    const size_t dyn = use_smem ? sizeof(unsigned int) * (size_t)n_polygons : 0;
+    if (dyn > 48 * 1024) GPL_CUDA(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_points, 512), (int64_t)kSMs * (use_smem ? 1 : 4)));
+    k_histogram<<<grid, 512, dyn, ctx->stream>>>(first_id, n_points, reinterpret_cast<unsigned long long *>(counts), n_polygons,
+                                                 use_smem ? 1 : 0);
+    ctx->launches++;
+    GPL_CUDA(cudaGetLastError());
     return GPL_OK;
 }
