@@ -142,18 +142,31 @@ def cpu_baseline_sample(n_sample: int, threads: int = 0):
     return n_sample / dt, cores, dt, int((first >= 0).sum())
 
 
+def best_cpu_threads(probe_points: int = 4_000_000) -> int:
+    """all logical CPUs or one per physical core, whichever runs the CPU join faster on a small probe
+    (the ring walk is latency bound; hyper-threads can hurt)"""
+    all_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best, best_rate = all_threads, 0.0
+    for th in sorted({all_threads, max(1, all_threads // 2)}, reverse=True):
+        rate, _, _, _ = cpu_baseline_sample(probe_points, th)
+        if rate > best_rate:
+            best, best_rate = th, rate
+    return best
+
+
 def run_reference(args, out=sys.stdout):
     """--impl reference: the reference's CPU path (restated: oracle/geo_oracle.c, kind 'port') on host cores."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return 0
     n_sample = args.ref_sample
+    best_threads = best_cpu_threads(min(n_sample, 4_000_000))
     for _ in range(args.warmup):
-        cpu_baseline_sample(min(n_sample, 500_000))
+        cpu_baseline_sample(min(n_sample, 500_000), best_threads)
     vals, times = [], []
-    cores = 0
+    cores = best_threads
     for _ in range(args.steps):
-        v, cores, dt, _hits = cpu_baseline_sample(n_sample)
+        v, cores, dt, _hits = cpu_baseline_sample(n_sample, best_threads)
         vals.append(v)
         times.append(dt)
     total_t = sum(times)
@@ -362,7 +375,7 @@ def _main(out):
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e["seconds"] / args.steps,
                        "path": "gpl_array_from_buffers(host) + gpl_pip_index_build + gpl_contains_join_host (pinned host points -> pinned host ids)"}
     if not args.no_cpu:
-        v, cores, dt, _ = cpu_baseline_sample(args.cpu_sample)
+        v, cores, dt, _ = cpu_baseline_sample(args.cpu_sample, best_cpu_threads())
         line["cpu_baseline"] = {"value": v, "unit": "geometries/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_sample} of {n} points x {N_POLYGONS} polygons in {dt:.2f} s, oracle/geo_oracle.c OpenMP (bbox grid + exact test)"}
     print(json.dumps(line), file=out, flush=True)
