@@ -702,7 +702,7 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     if (qy < 0.0f || !(tq < (float)(nb + 1))) return false;
     const int32_t b = min((int32_t)tq, nb - 1);
     const float4 *rec = fast + (int64_t)l.bucket_base + (int64_t)b * C;
-    const float height = l.inv_hf > 0.0f ? (float)nb / l.inv_hf : 0.0f;
+    const float height = l.inv_hf > 0.0f ? __fdividef((float)nb, l.inv_hf) : 0.0f;  // 2 ulp is plenty: R only feeds bounds with 2x slack
     const float R = fmaxf(l.xmaxf - l.xminf, height);
     const float eta = 9.5367431640625e-07f * R;                          // 2^-20 R
     const float B = 1.01f * (8.5f * eta * R + 1.9073486328125e-06f * R * R);  // eta*8.5R + 2^-19 R^2
@@ -720,7 +720,7 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     const int32_t count = __float_as_int(r[0].x);
 #pragma unroll
     for (int j = 1; j < 8; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
-    for (int32_t k = 8; k <= count; k += 8) {  // records 8.. (edge index k-1): only for lists longer than 7
+    for (int32_t k = 8; k <= count; k += 8) {  // records 8.. : only for lists longer than 7
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             r[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
@@ -910,13 +910,20 @@ __global__ void __launch_bounds__(512) k_histogram(const int32_t *__restrict__ i
         for (int64_t b = threadIdx.x; b < n_polys; b += blockDim.x) s_bins[b] = 0u;
         __syncthreads();
     }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int32_t id = __ldcs(ids + i);
+    auto add = [&](int32_t id) {
         if (id >= 0 && id < n_polys) {
             if (use_smem) atomicAdd(&s_bins[id], 1u);
             else atomicAdd(&counts[id], 1ULL);
         }
+    };
+    // four ids per thread and iteration (one 128-bit load; cudaMalloc'd columns are 16-byte aligned)
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(ids) & 15) == 0) ? n / 4 : 0;
+    const int4 *ids4 = reinterpret_cast<const int4 *>(ids);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 v = __ldcs(ids4 + i);
+        add(v.x), add(v.y), add(v.z), add(v.w);
     }
+    for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) add(__ldcs(ids + i));
     if (use_smem) {
         __syncthreads();
         for (int64_t b = threadIdx.x; b < n_polys; b += blockDim.x) {
@@ -1204,8 +1211,9 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         ctx->launches += 4;
         CUDAF(cudaGetLastError());
     }
-    // scratch used by the kernels above goes back to the cache only after they have run
-    CUDAF(cudaStreamSynchronize(st));
+    // No final synchronize: the scratch buffers above return to the context cache, which only ever hands them
+    // to work enqueued later on this same stream (stream-ordered reuse), and every consumer of the index
+    // launches on this stream too.
     l2_pin(idx, true);
     *out = idx;
     return GPL_OK;
@@ -1375,7 +1383,8 @@ extern "C" int gpl_join_histogram(gpl_ctx *ctx, const int32_t *first_id, int64_t
     const bool use_smem = n_polygons <= kHistSmemBins;
     const size_t dyn = use_smem ? sizeof(unsigned int) * (size_t)n_polygons : 0;
     if (dyn > 48 * 1024) GPL_CUDA(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_points, 512), (int64_t)kSMs * (use_smem ? 1 : 4)));
+    const int per_sm = use_smem ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(dyn, 1))) : 4;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_points, 2048), (int64_t)kSMs * per_sm));
     k_histogram<<<grid, 512, dyn, ctx->stream>>>(first_id, n_points, reinterpret_cast<unsigned long long *>(counts), n_polygons,
                                                  use_smem ? 1 : 0);
     ctx->launches++;

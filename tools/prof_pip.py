@@ -22,3 +22,13 @@ with torch.cuda.stream(st):
             e0.record(st); idx.query_device(pts.data_ptr(), n, ids.data_ptr()); e1.record(st); st.synchronize()
             print("  query ms", e0.elapsed_time(e1))
         t0=time.perf_counter(); idx.free(); t1=time.perf_counter(); print("free ms",(t1-t0)*1e3)
+
+    # per-polygon hit histogram (the N>1 step adds it)
+    idx=E.PipIndex(polys)
+    idx.query_device(pts.data_ptr(), n, ids.data_ptr())
+    counts=torch.zeros(10000,dtype=torch.int64,device=dev)
+    e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    for k in range(3):
+        counts.zero_()
+        e0.record(st); E.check(ctx.lib.gpl_join_histogram(ctx._h, ids.data_ptr(), n, counts.data_ptr(), 10000, E.GPL_DEVICE)); e1.record(st); st.synchronize()
+        print("  histogram ms", e0.elapsed_time(e1), int(counts.sum().item()))
