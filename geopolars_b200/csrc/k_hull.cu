@@ -9,15 +9,14 @@
 // memory (coalesced LDG.128), permuted in place there exactly like geo permutes its Vec, and the
 // recursion hull_set(a, b, slice) runs as an explicit stack machine whose control flow is warp-uniform:
 //   * farthest point: lanes stride over the slice, warp arg-max (value, then LAST index: Iterator::max_by);
-//   * partition by is_ccw: lanes evaluate the exact predicate for 32 elements at a time, __ballot_sync
-//     + popc give each element its destination (stable: trues keep their order at the front);
+//   * partition by is_ccw: lanes evaluate the exact predicate for 32 elements at a time; __ballot_sync + popc
+//     ranks reproduce geo's in-place Hoare partition as a set of disjoint swaps;
 //   * the second recursive call is a tail call, so a frame is pushed only for the first one.
 // Output rings have data-dependent length: pass 1 counts vertices per geometry, an exclusive scan turns
 // counts into ring offsets, pass 2 re-runs the same deterministic machine and writes coordinates.
-// Parity note: geo partitions with an unstable Hoare scheme, so the ORDER of elements inside a slice
-// differs from ours; that order only matters when two distinct points tie exactly for "farthest" —
-// then geo's pick depends on its slice order.  Tie-free inputs (and ties between identical
-// coordinates, e.g. the ring's closing duplicate) give bit-identical rings.  DESIGN.md "convex_hull".
+// Parity note: the slice permutations (swap_remove_to_first, the Hoare partition_slice) are reproduced element
+// for element, so even exact ties for "farthest" resolve like the restated geo code (Iterator::max_by keeps the
+// LAST maximal element of the slice).  DESIGN.md "convex_hull".
 #include <math.h>
 
 #include "common.cuh"
@@ -35,29 +34,57 @@ struct HullFrame {  // pending "emit far, then hull_set(a, far, slice)" after th
 __device__ __forceinline__ bool lex_less(double2 a, double2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
 __device__ __forceinline__ bool is_ccw(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
 
-// stable partition of P[s, s+len) by is_ccw(a, b, .): trues to the front (order kept), falses after
-// (order kept).  tmp is a scratch area of at least len elements.  Returns the number of trues.
+// geo's utils::partition_slice on P[s, s+len) with predicate is_ccw(a, b, .): an in-place Hoare scheme
+//     loop { while l < len && pred(l) { l++ }  while r > 0 && !pred(r) { r-- }  if l >= r { return l }  swap(l, r) }
+// whose result is fully determined by the predicate bits: with T = number of trues, the i-th FALSE element
+// (ascending) among positions < T is swapped with the i-th TRUE element counted from the right among
+// positions >= T; every other element stays where it is.  That is what the warp does: predicate ballots
+// (one exact orient2d per element), ranks from popc prefix counts, the two position lists in scratch, then
+// disjoint pairwise swaps.  The slice order therefore equals geo's element for element, which matters only
+// for the arg-max tie rule of hull_set.  `scratch` holds at least len int32 (it is the tmp buffer).
+// Returns T.
 __device__ __forceinline__ int32_t partition_ccw(double2 *P, double2 *tmp, int32_t s, int32_t len, double2 a, double2 b, int lane) {
     if (len <= 0) return 0;
-    int32_t n_true = 0, n_false = 0;
-    // pass 1: trues compacted into tmp[0..T), falses into tmp[len-1 .. ] from the back in REVERSE so that one
-    // pass suffices; pass 2 copies back, un-reversing the falses.
+    int32_t *scratch = reinterpret_cast<int32_t *>(tmp);  // [0, len): left-false positions, [len, 2 len): right-true positions
+    unsigned *masks = reinterpret_cast<unsigned *>(scratch + 2 * len);  // one ballot per 32 elements
+    const unsigned below = (1u << lane) - 1u;
+    int32_t n_true = 0;
     for (int32_t c = 0; c < len; c += 32) {
         const int32_t i = c + lane;
-        const bool in = i < len;
-        double2 q = in ? P[s + i] : make_double2(0.0, 0.0);
-        const bool t = in && is_ccw(a, b, q);
-        const unsigned mt = __ballot_sync(0xffffffffu, t), mf = __ballot_sync(0xffffffffu, in && !t);
-        const unsigned below = (1u << lane) - 1u;
-        if (t) tmp[n_true + __popc(mt & below)] = q;
-        if (in && !t) tmp[len - 1 - (n_false + __popc(mf & below))] = q;
+        const bool t = i < len && is_ccw(a, b, P[s + i]);
+        const unsigned mt = __ballot_sync(0xffffffffu, t);
+        if (lane == 0) masks[c >> 5] = mt;
         n_true += __popc(mt);
-        n_false += __popc(mf);
     }
     __syncwarp();
-    for (int32_t i = lane; i < len; i += 32) P[s + i] = i < n_true ? tmp[i] : tmp[len - 1 - (i - n_true)];
+    const int32_t T = n_true;
+    int32_t trues_before = 0;
+    for (int32_t c = 0; c < len; c += 32) {
+        const int32_t i = c + lane;
+        const unsigned mt = masks[c >> 5];
+        const bool in = i < len, t = (mt >> lane) & 1u;
+        const int32_t tb = trues_before + __popc(mt & below);  // trues in [0, i)
+        if (in && !t && i < T) scratch[i - tb] = i;                       // rank among left falses = falses in [0, i)
+        if (in && t && i >= T) scratch[len + (T - tb - 1)] = i;           // rank from the right = trues in (i, len)
+        trues_before += __popc(mt);
+    }
     __syncwarp();
-    return n_true;
+    // number of misplaced pairs = falses among the first T positions
+    int32_t falses_left = 0;
+    for (int32_t c = 0; c < T; c += 32) {
+        const unsigned mt = masks[c >> 5];
+        const int32_t width = min(32, T - c);
+        const unsigned valid = width == 32 ? 0xffffffffu : ((1u << width) - 1u);
+        falses_left += __popc(~mt & valid);
+    }
+    for (int32_t i = lane; i < falses_left; i += 32) {
+        const int32_t f = scratch[i], t = scratch[len + i];
+        const double2 x = P[s + f];
+        P[s + f] = P[s + t];
+        P[s + t] = x;
+    }
+    __syncwarp();
+    return T;
 }
 
 // index (within the slice) of the farthest point from segment a-b: max of p_orth . (p - a), LAST maximal element

@@ -82,3 +82,25 @@ def test_hull_vertex_set_against_exact_referee(ctx):
         n = len(ring) - 1
         for k in range(n):
             assert exact.orient_sign(tuple(ring[k]), tuple(ring[(k + 1) % n]), tuple(ring[(k + 2) % n])) > 0
+
+
+def test_exact_ties_follow_geo_slice_order(ctx, og, conv):
+    """integer lattices, regular polygons with duplicated and collinear points: many EXACT ties for the farthest
+    point.  The result then depends on geo's in-place slice permutations (Hoare partition, swap_remove_to_first,
+    max_by = last maximum); the kernel reproduces them, so the rings must still be identical to the oracle's."""
+    rng = np.random.default_rng(11)
+    shapes = []
+    for n in (3, 4, 5, 7, 9, 12):
+        g = np.stack(np.meshgrid(np.arange(n), np.arange(n)), -1).reshape(-1, 2).astype(float)
+        for rep in range(6):
+            shapes.append(rng.permutation(g).tolist())
+    for k in range(40):  # random small-integer clouds with repeats
+        m = int(rng.integers(4, 90))
+        shapes.append(rng.integers(-3, 4, size=(m, 2)).astype(float).tolist())
+    # points on a circle of radius 5 with integer coordinates + midpoints (collinear runs on the hull)
+    circ = [(5, 0), (4, 3), (3, 4), (0, 5), (-3, 4), (-4, 3), (-5, 0), (-4, -3), (-3, -4), (0, -5), (3, -4), (4, -3)]
+    mids = [((a[0] + b[0]) / 2, (a[1] + b[1]) / 2) for a, b in zip(circ, circ[1:] + circ[:1])]
+    for rep in range(10):
+        shapes.append(rng.permutation(np.array(circ + mids + circ, float)).tolist())
+    arr = GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, shapes)
+    _check(ctx, og, conv, arr)
