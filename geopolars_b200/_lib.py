@@ -95,6 +95,7 @@ SIGNATURES = {
     "gpl_ctx_set_stream": (_INT, [_P, _P]),
     "gpl_ctx_synchronize": (_INT, [_P]),
     "gpl_ctx_destroy": (None, [_P]),
+    "gpl_ctx_trim": (_INT, [_P]),
     "gpl_ctx_launch_count": (_I64, [_P]),
     "gpl_host_alloc": (_INT, [C.c_size_t, C.POINTER(_P)]),
     "gpl_host_free": (None, [_P]),

@@ -175,6 +175,13 @@ extern "C" void gpl_ctx_destroy(gpl_ctx *ctx) {
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+extern "C" int gpl_ctx_trim(gpl_ctx *ctx) {
+    GPL_REQUIRE(ctx != nullptr, GPL_ERR_INVALID_ARG, "ctx is NULL");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // cached blocks may still be in use by enqueued work
+    ctx->trim();
+    return GPL_OK;
+}
 extern "C" int64_t gpl_ctx_launch_count(const gpl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int gpl_host_alloc(size_t bytes, void **out) {

@@ -39,6 +39,10 @@ class Context:
     def synchronize(self) -> None:
         check(self.lib.gpl_ctx_synchronize(self._h))
 
+    def trim(self) -> None:
+        """return the allocator's cached free blocks to the driver"""
+        check(self.lib.gpl_ctx_trim(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.gpl_ctx_launch_count(self._h))

@@ -120,6 +120,8 @@ int gpl_ctx_create(int device, void *stream, gpl_ctx **out);
 int gpl_ctx_set_stream(gpl_ctx *ctx, void *stream);
 int gpl_ctx_synchronize(gpl_ctx *ctx);
 void gpl_ctx_destroy(gpl_ctx *ctx);
+/* give the cached (free) device blocks of the context's allocator back to the driver */
+int gpl_ctx_trim(gpl_ctx *ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 int64_t gpl_ctx_launch_count(const gpl_ctx *ctx);
 /* pinned host memory for truly asynchronous H2D/D2H */
