@@ -32,7 +32,16 @@ struct HullFrame {  // pending "emit far, then hull_set(a, far, slice)" after th
 };
 
 __device__ __forceinline__ bool lex_less(double2 a, double2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
-__device__ __forceinline__ bool is_ccw(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
+static __device__ __noinline__ bool is_ccw_exact(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
+// strict-CCW test.  The stage-A filter decides almost every call inline; only an uncertified determinant takes
+// the out-of-line adaptive predicate (keeps the hot loops small: 122 -> ~80 registers).
+__device__ __forceinline__ bool is_ccw(double2 a, double2 b, double2 c) {
+    const double dl = (a.x - c.x) * (b.y - c.y);
+    const double dr = (a.y - c.y) * (b.x - c.x);
+    const double det = dl - dr;
+    if (fabs(det) > kCcwA * (fabs(dl) + fabs(dr))) return det > 0.0;
+    return is_ccw_exact(a, b, c);
+}
 
 // geo's utils::partition_slice on P[s, s+len) with predicate is_ccw(a, b, .): an in-place Hoare scheme
 //     loop { while l < len && pred(l) { l++ }  while r > 0 && !pred(r) { r-- }  if l >= r { return l }  swap(l, r) }
@@ -256,22 +265,30 @@ __global__ void k_hull_max_len(int type, int64_t n_geoms, const int64_t *__restr
     if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
 }
 
-// One warp per geometry.  The staging area (points, scratch, frame stack) is in shared memory when the
-// largest geometry fits (cap_smem coordinates per warp), otherwise in a per-warp global workspace.
-template <bool WRITE>
-__global__ void __launch_bounds__(kHullWarps * 32) k_hull(int type, int64_t n_geoms, const double2 *__restrict__ xy,
-                                                          const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
-                                                          const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
-                                                          int32_t cap, int use_smem, uint8_t *__restrict__ workspace,
-                                                          int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
-                                                          double2 *__restrict__ out_xy) {
+// One warp per geometry.  The staging area (points + partition scratch) is in shared memory when the largest
+// geometry fits (SMEM = true: the pointers are derived from the __shared__ array only, so the compiler emits
+// LDS/STS instead of generic loads), otherwise in a per-warp global workspace.  The frame stack (one push
+// and one pop per hull_set call) always lives in the global workspace.
+template <bool WRITE, bool SMEM>
+__global__ void __launch_bounds__(kHullWarps * 32, SMEM ? 5 : 2) k_hull(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+                                                                        const int64_t *__restrict__ geom_off,
+                                                                        const int64_t *__restrict__ part_off,
+                                                                        const int64_t *__restrict__ ring_off,
+                                                                        const uint8_t *__restrict__ validity, int32_t cap,
+                                                                        uint8_t *__restrict__ workspace, int64_t *__restrict__ counts,
+                                                                        const int64_t *__restrict__ out_off, double2 *__restrict__ out_xy) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)cap * (2 * sizeof(double2) + sizeof(HullFrame));
-    uint8_t *base = use_smem ? smem + wid * per_warp : workspace + ((size_t)blockIdx.x * kHullWarps + wid) * per_warp;
-    double2 *P = reinterpret_cast<double2 *>(base);
-    double2 *tmp = P + cap;
-    HullFrame *stack = reinterpret_cast<HullFrame *>(tmp + cap);
+    const size_t warp_slot = (size_t)blockIdx.x * kHullWarps + wid;
+    const size_t stack_bytes = (size_t)cap * sizeof(HullFrame), stage_bytes = (size_t)cap * 2 * sizeof(double2);
+    HullFrame *stack = reinterpret_cast<HullFrame *>(workspace + warp_slot * (stack_bytes + (SMEM ? 0 : stage_bytes)));
+    double2 *P, *tmp;
+    if (SMEM) {
+        P = reinterpret_cast<double2 *>(smem) + (size_t)wid * 2 * cap;
+    } else {
+        P = reinterpret_cast<double2 *>(workspace + warp_slot * (stack_bytes + stage_bytes) + stack_bytes);
+    }
+    tmp = P + cap;
     const int64_t n_warps = (int64_t)gridDim.x * kHullWarps;
     for (int64_t g = (int64_t)blockIdx.x * kHullWarps + wid; g < n_geoms; g += n_warps) {
         Emitter<WRITE> em;
@@ -379,21 +396,35 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     GPL_REQUIRE(h_max < (1ULL << 30), GPL_ERR_UNSUPPORTED, "convex_hull: a geometry with %llu coordinates is too large", h_max);
     const int32_t cap = (int32_t)std::max<unsigned long long>(h_max, 4);
-    const size_t per_warp = (size_t)cap * (2 * sizeof(double2) + sizeof(HullFrame));
-    const size_t smem_bytes = per_warp * kHullWarps;
+    const size_t stage_bytes = (size_t)cap * 2 * sizeof(double2), stack_bytes = (size_t)cap * sizeof(HullFrame);
+    const size_t smem_bytes = stage_bytes * kHullWarps;
     const bool use_smem = smem_bytes <= 200 * 1024;
     int grid;
     Scratch<uint8_t> workspace;
     if (use_smem) {
-        GPL_CUDA(cudaFuncSetAttribute(k_hull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem_bytes, 1)));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (220 * 1024) / std::max<size_t>(smem_bytes, 1)));
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), kHullWarps), (int64_t)kSMs * per_sm));
     } else {
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), kHullWarps), (int64_t)kSMs * 2));
-        GPL_TRY(workspace.get(ctx, per_warp * kHullWarps * (size_t)grid));
     }
+    GPL_TRY(workspace.get(ctx, (stack_bytes + (use_smem ? 0 : stage_bytes)) * kHullWarps * (size_t)grid));
     const size_t dyn = use_smem ? smem_bytes : 0;
+    // pass: 0 = count only, 1 = write.  `off`/`dst` are the ring offsets and the output buffer of a writing pass.
+    auto launch = [&](bool write, int64_t *cnt, const int64_t *off, double2 *dst) -> int {
+        if (n == 0) return GPL_OK;
+        if (use_smem) {
+            if (write) k_hull<true, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+            else k_hull<false, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+        } else {
+            if (write) k_hull<true, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+            else k_hull<false, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+        }
+        ctx->launches++;
+        GPL_CUDA(cudaGetLastError());
+        return GPL_OK;
+    };
     Scratch<int64_t> ring_off, geom_off;
     GPL_TRY(ring_off.get(ctx, (size_t)n + 1));
     GPL_TRY(geom_off.get(ctx, (size_t)n + 1));
@@ -416,11 +447,7 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         GPL_TRY(tmp_off.get(ctx, (size_t)n + 1));
         GPL_LAUNCH(ctx, k_hull_upper, (int)ceil_div(n, 256), 256, 0, in->type, n, in->geom_off, in->part_off, in->ring_off, ub.p);
         GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, ub.p, n, tmp_off.p, nullptr)));
-        k_hull<true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
-                                                                  cap, use_smem ? 1 : 0, workspace.p, counts.p, tmp_off.p,
-                                                                  reinterpret_cast<double2 *>(tmp.p));
-        ctx->launches++;
-        GPL_CUDA(cudaGetLastError());
+        GPL_TRY(launch(true, counts.p, tmp_off.p, reinterpret_cast<double2 *>(tmp.p)));
         GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
         GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         GPL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -430,28 +457,15 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
                    reinterpret_cast<double2 *>(oxy.p));
         GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp returns to the cache when this scope ends
     } else {
-        if (n > 0) {
-            k_hull<false><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
-                                                                       in->validity, cap, use_smem ? 1 : 0, workspace.p, counts.p, nullptr,
-                                                                       nullptr);
-            ctx->launches++;
-            GPL_CUDA(cudaGetLastError());
-        }
+        GPL_TRY(launch(false, counts.p, nullptr, nullptr));
         GPL_TRY((exclusive_scan<int64_t, int64_t>(ctx, counts.p, n, ring_off.p, total.p)));
         GPL_CUDA(cudaMemcpyAsync(&h_total, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         GPL_CUDA(cudaStreamSynchronize(ctx->stream));
         GPL_TRY(oxy.get(ctx, (size_t)h_total * 2));
-        if (n > 0) {
-            k_hull<true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
-                                                                      in->validity, cap, use_smem ? 1 : 0, workspace.p, nullptr, ring_off.p,
-                                                                      reinterpret_cast<double2 *>(oxy.p));
-            ctx->launches++;
-            GPL_CUDA(cudaGetLastError());
-        }
+        GPL_TRY(launch(true, nullptr, ring_off.p, reinterpret_cast<double2 *>(oxy.p)));
     }
     // geom_off = identity: geometry i owns ring i (a null input row becomes an empty, null polygon)
     GPL_LAUNCH(ctx, k_iota, (int)ceil_div(n + 1, 256), 256, 0, geom_off.p, n + 1);
-    if (workspace.p) GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // workspace returns to the cache below
     gpl_array *o = array_new(ctx, GPL_POLYGON);
     o->n_geoms = n, o->n_rings = n, o->n_coords = h_total;
     o->xy = oxy.take(), o->own_xy = true;

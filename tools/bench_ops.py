@@ -91,7 +91,7 @@ def main():
 
         t = timed(st, hull, reps=3, warm=1)
         hv = keep["h"].view()
-        row("convex_hull (config 5, two passes)", G, "polygons", 2 * nc * 16, hv.n_coords * 16, *t)
+        row("convex_hull (config 5)", G, "polygons", nc * 16, hv.n_coords * 16, *t)
         res["hull_mean_vertices"] = hv.n_coords / G
         keep.clear()
         del polys, xy, ro, go, out_f
