@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts,
                                                       const int64_t *__restrict__ ring_off,
                                                       const uint8_t *__restrict__ validity,
                                                       const int32_t *__restrict__ parent, PartHeader *__restrict__ parts,
-                                                      int32_t *__restrict__ nb_out) {
+                                                      int32_t *__restrict__ nb_out, int64_t *__restrict__ any_holes) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts,
             h.flags = (valid ? 2 : 0) | ((r1 - r0 > 1) ? 1 : 0);
             parts[p] = h;
             nb_out[p] = (int32_t)nb;
+            if (valid && r1 - r0 > 1) *any_holes = 1;  // benign race: every writer stores the same value
         }
     }
 }
@@ -1083,8 +1084,9 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         parent_p = parent.p;
     }
     const int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Pa, 8), (int64_t)kSMs * 8));
+    CUDAF(cudaMemsetAsync(totals.p, 0, sizeof(int64_t) * 8, st));
     k_part_headers<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, polys->validity,
-                                          parent_p, hdr.p, nb.p);
+                                          parent_p, hdr.p, nb.p, totals.p + 4);
     ctx->launches++;
     CUDAF(cudaGetLastError());
 
@@ -1131,8 +1133,8 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, fast_slots.p, P, fast_base.p, totals.p + 3)));
 
     // the data-dependent sizes + the grid parameters: one small D2H (index build is once per join)
-    int64_t h_tot[4];
-    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 4, cudaMemcpyDeviceToHost, st));
+    int64_t h_tot[5];
+    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, st));
     CUDAF(cudaMemcpyAsync(&idx->grid, gp.p, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
     CUDAF(cudaStreamSynchronize(st));
     idx->n_overflow = h_tot[0];  // all cell items
@@ -1144,7 +1146,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
                   (long long)idx->n_overflow);
         return fail(GPL_ERR_UNSUPPORTED);
     }
-    idx->any_holes = polys->n_rings > P;
+    idx->any_holes = h_tot[4] != 0;  // set on the device: ring counts alone cannot tell (an empty polygon next to one with a hole)
     idx->multi = type == GPL_MULTIPOLYGON;
 
     // ---- phase 2: one slab, filled in place ----------------------------------------------------------

@@ -140,3 +140,18 @@ def test_large_rings_overlapping_boxes_and_deferred_overflow(ctx, og, conv):
     wf, wc = og.contains_join(conv(stars), on_edges, use_grid=True, threads=0)
     f2, c2 = PipIndex(ctx.upload(stars)).query(on_edges, with_count=True)
     assert np.array_equal(f2, wf) and np.array_equal(c2, wc)
+
+
+def test_empty_polygon_next_to_polygon_with_hole(ctx, og, conv):
+    """ring count == polygon count although a hole exists: the hole table must still be built"""
+    from geopolars_b200.engine import PipIndex
+
+    sq = [(0, 0), (10, 0), (10, 10), (0, 10), (0, 0)]
+    hole = [(4, 4), (4, 6), (6, 6), (6, 4), (4, 4)]
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[], [sq, hole]])
+    assert polys.n_rings == len(polys) == 2
+    g = np.linspace(-1, 11, 49)
+    pts = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    want, wc = og.contains_join(conv(polys), pts, use_grid=False)
+    first, cnt = PipIndex(ctx.upload(polys)).query(pts, with_count=True)
+    assert np.array_equal(first, want) and np.array_equal(cnt, wc) and (want == 1).any() and (want == -1).any()
