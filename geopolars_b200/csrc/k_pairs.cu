@@ -58,8 +58,10 @@ __device__ __forceinline__ bool line_intersects_line(double2 s0, double2 e0, dou
     return false;
 }
 
-// LineString x LineString intersects, warp cooperative.  Result is warp-uniform.
-__device__ __forceinline__ bool ls_intersects_ls(Coords A, int64_t na, Coords B, int64_t nb, int lane) {
+// LineString x LineString intersects, warp cooperative.  Result is warp-uniform.  CA / CB: anything indexable
+// that yields double2 (Coords, Chain).
+template <class CA, class CB>
+__device__ __forceinline__ bool ls_intersects_ls(CA A, int64_t na, CB B, int64_t nb, int lane) {
     if (na < 2 || nb < 2) return false;  // no lines() on either side
     // has_disjoint_bboxes
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -105,7 +107,8 @@ __device__ __forceinline__ double seg_dist2(double2 p, double2 s, double2 e) {
     return (cross * cross) / dd;
 }
 
-__device__ __forceinline__ double ls_ls_min_dist2(Coords A, int64_t na, Coords B, int64_t nb, int lane) {
+template <class CA, class CB>
+__device__ __forceinline__ double ls_ls_min_dist2(CA A, int64_t na, CB B, int64_t nb, int lane) {
     const double big = 1.7976931348623157e308;
     double best = big;
     const int64_t sa = na - 1, sb = nb - 1;
@@ -466,6 +469,279 @@ __device__ __forceinline__ void polygon_position(const double2 *__restrict__ xy,
     inside = true;
 }
 
+
+// ---- generic row-wise intersects: every pair of GeoArrow types --------------------------------------------
+// geo 0.27 intersects/{coordinate,line,line_string,polygon,collections}.rs (recalled).  The boolean is decided
+// by exact predicates only, so any exact decision procedure gives geo's answer on valid input; the parts of
+// geo's procedure that are NOT neutral on invalid input (polygon-level rejects use the EXTERIOR ring's box,
+// Polygon x Coord is `exterior != Outside && no hole strictly contains it`, Polygon x Polygon tests all rings
+// of `other` against `self` but only self's exterior against `other`) are reproduced as they are.
+// One shortcut is taken: where geo tests every vertex of a chain against a polygon after all segment pairs
+// failed, the first vertex is tested — with no crossing of any ring the chain lies in one face of the ring
+// arrangement, so all its vertices give the same answer (the oracle tests every vertex, the tests compare).
+struct Chain {  // a linestring, or a ring with Polygon::new's closing coordinate emulated
+    const double2 *p;
+    int64_t n;
+    bool closing;
+    __device__ __forceinline__ int64_t coords() const { return n + (closing ? 1 : 0); }
+    __device__ __forceinline__ double2 operator[](int64_t i) const { return p[i < n ? i : 0]; }
+};
+__device__ __forceinline__ Chain make_line(const double2 *xy, int64_t c0, int64_t c1) { return Chain{xy + c0, c1 - c0, false}; }
+__device__ __forceinline__ Chain make_ring(const double2 *xy, int64_t c0, int64_t c1) {
+    const int64_t n = c1 - c0;
+    bool closing = false;
+    if (n >= 2) {
+        const double2 f = xy[c0], l = xy[c1 - 1];
+        closing = !(f.x == l.x && f.y == l.y);
+    }
+    return Chain{xy + c0, n, closing};
+}
+struct Box {
+    double x0, y0, x1, y1;
+    bool has;
+};
+__device__ __forceinline__ Box chain_box(const Chain &c, int lane) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    Box b{inf, inf, -inf, -inf, c.n > 0};
+    for (int64_t i = lane; i < c.n; i += 32) {
+        const double2 q = c.p[i];
+        b.x0 = fmin(b.x0, q.x), b.y0 = fmin(b.y0, q.y), b.x1 = fmax(b.x1, q.x), b.y1 = fmax(b.y1, q.y);
+    }
+    b.x0 = warp_min(b.x0), b.y0 = warp_min(b.y0), b.x1 = warp_max(b.x1), b.y1 = warp_max(b.y1);
+    return b;
+}
+// has_disjoint_bboxes: only when both sides have a box
+__device__ __forceinline__ bool boxes_disjoint(const Box &a, const Box &b) {
+    return a.has && b.has && (a.x0 > b.x1 || b.x0 > a.x1 || a.y0 > b.y1 || b.y0 > a.y1);
+}
+
+struct Side {
+    int type;
+    const double2 *xy;
+    const int64_t *go, *po, *ro;
+};
+__device__ __forceinline__ int side_class(int t) { return (t == GPL_POINT || t == GPL_MULTIPOINT) ? 0 : (t == GPL_LINESTRING || t == GPL_MULTILINESTRING) ? 1 : 2; }
+// sub-geometries of row r: points [lo,hi) of class 0; chains of class 1; polygon parts of class 2
+__device__ __forceinline__ void side_range(const Side &s, int64_t r, int64_t &lo, int64_t &hi) {
+    if (s.type == GPL_POINT) lo = r, hi = r + 1;
+    else if (s.type == GPL_LINESTRING || s.type == GPL_POLYGON) lo = 0, hi = 1;
+    else lo = s.go[r], hi = s.go[r + 1];
+}
+__device__ __forceinline__ Chain side_chain(const Side &s, int64_t r, int64_t k) {
+    if (s.type == GPL_LINESTRING) return make_line(s.xy, s.go[r], s.go[r + 1]);
+    return make_line(s.xy, s.ro[k], s.ro[k + 1]);
+}
+__device__ __forceinline__ void side_part(const Side &s, int64_t r, int64_t q, int64_t &r0, int64_t &r1) {
+    if (s.type == GPL_POLYGON) r0 = s.go[r], r1 = s.go[r + 1];
+    else r0 = s.po[q], r1 = s.po[q + 1];
+}
+__device__ __forceinline__ Chain part_ring(const Side &s, int64_t ring) { return make_ring(s.xy, s.ro[ring], s.ro[ring + 1]); }
+
+// impl Intersects<Coord> for Polygon: exterior != Outside && all holes != Inside
+__device__ __forceinline__ bool polygon_intersects_coord(const Side &s, int64_t r0, int64_t r1, double2 p, int lane) {
+    if (r1 <= r0) return false;
+    if (ring_position(s.xy, s.ro[r0], s.ro[r0 + 1] - s.ro[r0], p, lane) == 0) return false;
+    for (int64_t h = r0 + 1; h < r1; ++h)
+        if (ring_position(s.xy, s.ro[h], s.ro[h + 1] - s.ro[h], p, lane) == 2) return false;
+    return true;
+}
+// chain (>= 1 line) against one polygon part; `reject_box`: geo's has_disjoint_bboxes(chain, polygon)
+__device__ __forceinline__ bool chain_intersects_polygon(const Chain &c, const Side &s, int64_t r0, int64_t r1, const Box &ext_box,
+                                                         bool reject_box, int lane) {
+    if (c.coords() < 2 || r1 <= r0) return false;  // no lines() / no exterior
+    if (reject_box && boxes_disjoint(chain_box(c, lane), ext_box)) return false;
+    for (int64_t rs = r0; rs < r1; ++rs) {
+        const Chain ring = part_ring(s, rs);
+        if (ls_intersects_ls(ring, ring.coords(), c, c.coords(), lane)) return true;
+    }
+    return polygon_intersects_coord(s, r0, r1, c[0], lane);
+}
+// impl Intersects<Polygon> for Polygon, self = S, polygon = O
+__device__ __forceinline__ bool polygon_intersects_polygon(const Side &S, int64_t s0, int64_t s1, const Side &O, int64_t o0, int64_t o1,
+                                                           int lane) {
+    if (s1 <= s0 || o1 <= o0) return false;
+    const Chain sext = part_ring(S, s0), oext = part_ring(O, o0);
+    const Box sbox = chain_box(sext, lane), obox = chain_box(oext, lane);
+    if (boxes_disjoint(sbox, obox)) return false;
+    // self.intersects(polygon.exterior()) || polygon.interiors().any(|r| self.intersects(r))
+    for (int64_t ro = o0; ro < o1; ++ro)
+        if (chain_intersects_polygon(part_ring(O, ro), S, s0, s1, sbox, ro > o0, lane)) return true;
+    // polygon.intersects(self.exterior()): its segment tests are a subset of the ones above
+    return sext.coords() >= 2 && polygon_intersects_coord(O, o0, o1, sext[0], lane);
+}
+
+__device__ __forceinline__ bool row_intersects(Side a, int64_t ra, Side b, int64_t rb, int lane) {
+    int ca = side_class(a.type), cb = side_class(b.type);
+    if (ca == 2 && cb == 2) {
+        int64_t pa0, pa1, pb0, pb1;
+        side_range(a, ra, pa0, pa1);
+        side_range(b, rb, pb0, pb1);
+        const bool self_is_a = b.type == GPL_POLYGON;  // (Multi)Polygon x Polygon: parts of a are `self`; x MultiPolygon: parts of b
+        for (int64_t p = pa0; p < pa1; ++p) {
+            int64_t s0, s1;
+            side_part(a, ra, p, s0, s1);
+            for (int64_t q = pb0; q < pb1; ++q) {
+                int64_t o0, o1;
+                side_part(b, rb, q, o0, o1);
+                if (self_is_a ? polygon_intersects_polygon(a, s0, s1, b, o0, o1, lane) : polygon_intersects_polygon(b, o0, o1, a, s0, s1, lane))
+                    return true;
+            }
+        }
+        return false;
+    }
+    if (ca > cb) {  // the remaining cases do not depend on which side is `self`
+        Side t = a; a = b; b = t;
+        int64_t tr = ra; ra = rb; rb = tr;
+        int tc = ca; ca = cb; cb = tc;
+    }
+    int64_t a0, a1, b0, b1;
+    side_range(a, ra, a0, a1);
+    side_range(b, rb, b0, b1);
+    if (ca == 0) {
+        for (int64_t i = a0; i < a1; ++i) {
+            const double2 p = a.xy[i];
+            if (cb == 0) {  // Point x Point: equality
+                bool hit = false;
+                for (int64_t j = b0 + lane; j < b1; j += 32) {
+                    const double2 q = b.xy[j];
+                    hit = hit || (q.x == p.x && q.y == p.y);
+                }
+                if (__any_sync(0xffffffffu, hit)) return true;
+            } else if (cb == 1) {  // lines().any(|l| l.intersects(coord))
+                for (int64_t k = b0; k < b1; ++k) {
+                    const Chain c = side_chain(b, rb, k);
+                    bool hit = false;
+                    for (int64_t j = lane; j + 1 < c.n; j += 32) hit = hit || line_intersects_coord(c.p[j], c.p[j + 1], p);
+                    if (__any_sync(0xffffffffu, hit)) return true;
+                }
+            } else {
+                for (int64_t q = b0; q < b1; ++q) {
+                    int64_t r0, r1;
+                    side_part(b, rb, q, r0, r1);
+                    if (polygon_intersects_coord(b, r0, r1, p, lane)) return true;
+                }
+            }
+        }
+        return false;
+    }
+    // ca == 1
+    for (int64_t k = a0; k < a1; ++k) {
+        const Chain c = side_chain(a, ra, k);
+        if (cb == 1) {
+            for (int64_t m = b0; m < b1; ++m) {
+                const Chain d = side_chain(b, rb, m);
+                if (ls_intersects_ls(c, c.n, d, d.n, lane)) return true;
+            }
+        } else {
+            for (int64_t q = b0; q < b1; ++q) {
+                int64_t r0, r1;
+                side_part(b, rb, q, r0, r1);
+                if (r1 <= r0) continue;
+                const Box ext = chain_box(part_ring(b, r0), lane);
+                if (chain_intersects_polygon(c, b, r0, r1, ext, true, lane)) return true;
+            }
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) k_intersects_generic(int64_t n, Side a, const uint8_t *__restrict__ av, Side b,
+                                                            const uint8_t *__restrict__ bv, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool res = false;
+        if (bit_get(av, r) && bit_get(bv, r)) res = row_intersects(a, r, b, r, lane);
+        if (lane == 0) out[r] = res ? 1 : 0;
+    }
+}
+
+// distance for LineString x Polygon, Polygon x LineString, Polygon x Polygon rows (geo 0.27
+// euclidean_distance.rs, recalled): 0 when the row intersects; a geometry lying strictly inside the other's
+// exterior (hence in a hole) is measured against the interior rings, everything else exterior to exterior /
+// linestring to exterior; each of those is the nearest-neighbour minimum over (vertex, segment) items.
+// geo's rotating-calipers branch for two convex polygons computes the same minimum (different roundings).
+__device__ __forceinline__ double chain_nn_dist2(const Chain &a, const Chain &b, int lane) {
+    return ls_ls_min_dist2(a, a.coords(), b, b.coords(), lane);
+}
+__global__ void __launch_bounds__(256) k_distance_generic(int64_t n, Side a, const uint8_t *__restrict__ av, Side b,
+                                                          const uint8_t *__restrict__ bv, double *__restrict__ out,
+                                                          uint8_t *__restrict__ out_valid) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double big = 1.7976931348623157e308;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool ok = bit_get(av, r) && bit_get(bv, r);
+        double d = nan("");
+        if (ok) {
+            // first chain of each side (the linestring, or the exterior ring) must have a line
+            int64_t a0 = a.go[r], a1 = a.go[r + 1], b0 = b.go[r], b1 = b.go[r + 1];
+            const bool pa = a.type == GPL_POLYGON, pb = b.type == GPL_POLYGON;
+            const Chain ea = pa ? (a1 > a0 ? part_ring(a, a0) : Chain{a.xy, 0, false}) : make_line(a.xy, a0, a1);
+            const Chain eb = pb ? (b1 > b0 ? part_ring(b, b0) : Chain{b.xy, 0, false}) : make_line(b.xy, b0, b1);
+            if (ea.n < 2 || eb.n < 2) {
+                ok = false;
+            } else if (row_intersects(a, r, b, r, lane)) {
+                d = 0.0;
+            } else {
+                double m = big;
+                bool done = false;
+                if (pa && a1 - a0 > 1 && ring_position(a.xy, a.ro[a0], a.ro[a0 + 1] - a.ro[a0], eb.p[0], lane) == 2) {
+                    for (int64_t h = a0 + 1; h < a1; ++h) m = fmin(m, chain_nn_dist2(eb, part_ring(a, h), lane));
+                    done = true;
+                } else if (pb && b1 - b0 > 1 && ring_position(b.xy, b.ro[b0], b.ro[b0 + 1] - b.ro[b0], ea.p[0], lane) == 2) {
+                    for (int64_t h = b0 + 1; h < b1; ++h) m = fmin(m, chain_nn_dist2(ea, part_ring(b, h), lane));
+                    done = true;
+                }
+                if (!done) m = chain_nn_dist2(ea, eb, lane);
+                d = sqrt(m);
+            }
+        }
+        if (lane == 0) {
+            out[r] = ok ? d : nan("");
+            if (out_valid) out_valid[r] = ok ? 1 : 0;
+        }
+    }
+}
+
+// impl Contains<Coord> for LineString (interior only: an end point counts only on a closed linestring);
+// MultiLineString: any member.  geo 0.27 contains/line_string.rs, contains/line.rs (recalled).
+__global__ void __launch_bounds__(256) k_lines_contain_point(int64_t n, Side a, const uint8_t *__restrict__ av,
+                                                             const double2 *__restrict__ pts, const uint8_t *__restrict__ pv,
+                                                             uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool res = false;
+        if (bit_get(av, r) && bit_get(pv, r)) {
+            const double2 p = pts[r];
+            int64_t k0, k1;
+            side_range(a, r, k0, k1);
+            for (int64_t k = k0; k < k1 && !res; ++k) {
+                const Chain c = side_chain(a, r, k);
+                if (c.n == 0) continue;
+                const double2 f = c.p[0], l = c.p[c.n - 1];
+                if ((p.x == f.x && p.y == f.y) || (p.x == l.x && p.y == l.y)) {
+                    res = (f.x == l.x && f.y == l.y);  // is_closed()
+                    continue;
+                }
+                bool hit = false;
+                for (int64_t i = lane; i + 1 < c.n; i += 32) {
+                    const double2 s = c.p[i], e = c.p[i + 1];
+                    const bool ps = (p.x == s.x && p.y == s.y), pe = (p.x == e.x && p.y == e.y);
+                    const bool in_line = (s.x == e.x && s.y == e.y) ? ps : (!ps && !pe && line_intersects_coord(s, e, p));
+                    hit = hit || in_line || (i > 0 && ps);
+                }
+                res = __any_sync(0xffffffffu, hit);
+            }
+        }
+        if (lane == 0) out[r] = res ? 1 : 0;
+    }
+}
+
 // poly rows vs point rows.  MODE 0: contains byte   MODE 1: distance
 template <int MODE>
 __global__ void __launch_bounds__(256) k_poly_point(int ptype, int64_t n, const double2 *__restrict__ pxy,
@@ -594,15 +870,21 @@ extern "C" int gpl_intersects(gpl_ctx *ctx, const gpl_array *a, const gpl_array 
     GPL_REQUIRE(ctx && a && b && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_intersects: NULL argument");
     GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "intersects: lengths differ (%lld vs %lld)",
                 (long long)a->n_geoms, (long long)b->n_geoms);
-    GPL_REQUIRE(a->type == GPL_LINESTRING && b->type == GPL_LINESTRING, GPL_ERR_INVALID_TYPE,
-                "Expected LineString x LineString (found %s x %s)", type_name(a->type), type_name(b->type));
+    GPL_REQUIRE(a->type >= GPL_POINT && a->type <= GPL_MULTIPOLYGON && a->type != GPL_LINEARRING && b->type >= GPL_POINT &&
+                    b->type <= GPL_MULTIPOLYGON && b->type != GPL_LINEARRING,
+                GPL_ERR_INVALID_TYPE, "intersects: unsupported geometry pair %s x %s", type_name(a->type), type_name(b->type));
     GPL_CUDA(cudaSetDevice(ctx->device));
     int64_t n = a->n_geoms;
     if (n == 0) return GPL_OK;
     Scratch<uint8_t> bytes, flag;
     GPL_TRY(bytes.get(ctx, (size_t)n));
-    GPL_TRY(flag.get(ctx, (size_t)n));
     const double2 *axy = reinterpret_cast<const double2 *>(a->xy), *bxy = reinterpret_cast<const double2 *>(b->xy);
+    if (!(a->type == GPL_LINESTRING && b->type == GPL_LINESTRING)) {  // every other pair: one warp per row, exact predicates
+        Side sa{a->type, axy, a->geom_off, a->part_off, a->ring_off}, sb{b->type, bxy, b->geom_off, b->part_off, b->ring_off};
+        GPL_LAUNCH(ctx, k_intersects_generic, warp_grid(n, 8), 256, 0, n, sa, a->validity, sb, b->validity, bytes.p);
+        return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
+    }
+    GPL_TRY(flag.get(ctx, (size_t)n));
     GPL_LAUNCH(ctx, k_ls_ls_fast<0>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,
                b->validity, bytes.p, nullptr, nullptr, flag.p);
     GPL_LAUNCH(ctx, k_ls_ls_exact<0>, warp_grid(ceil_div(n, 32), kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, bxy, b->geom_off,
@@ -614,14 +896,22 @@ extern "C" int gpl_contains(gpl_ctx *ctx, const gpl_array *polygons, const gpl_a
     GPL_REQUIRE(ctx && polygons && points && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_contains: NULL argument");
     GPL_REQUIRE(polygons->n_geoms == points->n_geoms, GPL_ERR_LENGTH_MISMATCH, "contains: lengths differ (%lld vs %lld)",
                 (long long)polygons->n_geoms, (long long)points->n_geoms);
-    GPL_REQUIRE((polygons->type == GPL_POLYGON || polygons->type == GPL_MULTIPOLYGON) && points->type == GPL_POINT,
-                GPL_ERR_INVALID_TYPE, "Expected (Multi)Polygon x Point (found %s x %s)", type_name(polygons->type),
+    const bool area = polygons->type == GPL_POLYGON || polygons->type == GPL_MULTIPOLYGON;
+    const bool lines = polygons->type == GPL_LINESTRING || polygons->type == GPL_MULTILINESTRING;
+    GPL_REQUIRE((area || lines) && points->type == GPL_POINT, GPL_ERR_INVALID_TYPE,
+                "Expected (Multi)Polygon or (Multi)LineString x Point (found %s x %s)", type_name(polygons->type),
                 type_name(points->type));
     GPL_CUDA(cudaSetDevice(ctx->device));
     int64_t n = polygons->n_geoms;
     if (n == 0) return GPL_OK;
     Scratch<uint8_t> bytes;
     GPL_TRY(bytes.get(ctx, (size_t)n));
+    if (lines) {
+        Side sl{polygons->type, reinterpret_cast<const double2 *>(polygons->xy), polygons->geom_off, polygons->part_off, polygons->ring_off};
+        GPL_LAUNCH(ctx, k_lines_contain_point, warp_grid(n, 8), 256, 0, n, sl, polygons->validity,
+                   reinterpret_cast<const double2 *>(points->xy), points->validity, bytes.p);
+        return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
+    }
     GPL_LAUNCH(ctx, k_poly_point<0>, warp_grid(n, 8), 256, 0, polygons->type, n, reinterpret_cast<const double2 *>(polygons->xy),
                polygons->geom_off, polygons->part_off, polygons->ring_off, polygons->validity,
                reinterpret_cast<const double2 *>(points->xy), points->validity, bytes.p, nullptr, nullptr);
@@ -633,8 +923,7 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
     GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "distance: lengths differ (%lld vs %lld)",
                 (long long)a->n_geoms, (long long)b->n_geoms);
     const int ta = a->type, tb = b->type;
-    bool ok = (ta == GPL_POINT && (tb == GPL_POINT || tb == GPL_LINESTRING || tb == GPL_POLYGON)) ||
-              (ta == GPL_LINESTRING && (tb == GPL_POINT || tb == GPL_LINESTRING)) || (ta == GPL_POLYGON && tb == GPL_POINT);
+    bool ok = (ta == GPL_POINT || ta == GPL_LINESTRING || ta == GPL_POLYGON) && (tb == GPL_POINT || tb == GPL_LINESTRING || tb == GPL_POLYGON);
     GPL_REQUIRE(ok, GPL_ERR_INVALID_TYPE, "distance: unsupported geometry pair %s x %s", type_name(ta), type_name(tb));
     GPL_CUDA(cudaSetDevice(ctx->device));
     int64_t n = a->n_geoms;
@@ -668,6 +957,9 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
     } else if (ta == GPL_POINT && tb == GPL_POLYGON) {
         GPL_LAUNCH(ctx, k_poly_point<1>, warp_grid(n, 8), 256, 0, b->type, n, bxy, b->geom_off, b->part_off, b->ring_off, b->validity,
                    axy, a->validity, nullptr, dst, vb);
+    } else if (tb != GPL_POINT) {  // LineString x Polygon, Polygon x LineString, Polygon x Polygon
+        Side sa{ta, axy, a->geom_off, a->part_off, a->ring_off}, sb{tb, bxy, b->geom_off, b->part_off, b->ring_off};
+        GPL_LAUNCH(ctx, k_distance_generic, warp_grid(n, 8), 256, 0, n, sa, a->validity, sb, b->validity, dst, vb);
     } else {
         GPL_LAUNCH(ctx, k_poly_point<1>, warp_grid(n, 8), 256, 0, a->type, n, axy, a->geom_off, a->part_off, a->ring_off, a->validity,
                    bxy, b->validity, nullptr, dst, vb);

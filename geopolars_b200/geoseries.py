@@ -220,10 +220,11 @@ class GeoRustSeries:
 
     # -- additions: binary predicates (planned-only in the reference docs, geoseries.rst:47-64) ----------
     def contains(self, other: GeoSeries):
-        """row-wise: self[i] (Polygon/MultiPolygon) contains other[i] (Point)"""
+        """row-wise: self[i] ((Multi)Polygon or (Multi)LineString) contains other[i] (Point)"""
         return _pa().array(E.contains(self._d(), other.device))
 
     def intersects(self, other: GeoSeries):
+        """row-wise geo `Intersects` for every pair of (Multi)Point / (Multi)LineString / (Multi)Polygon columns"""
         return _pa().array(E.intersects(self._d(), other.device))
 
 

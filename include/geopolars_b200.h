@@ -187,11 +187,16 @@ int gpl_euclidean_length(gpl_ctx *ctx, const gpl_array *in, double *out, int mem
  * geo's quick_hull vertex order */
 int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
 /* GeoSeries::distance (geoseries.rs:141-146), row-wise 1:1; out[n] f64, out_validity bitmap
- * (may be NULL) */
+ * (may be NULL).  Pairs: any of Point / LineString / Polygon on either side (geo EuclideanDistance);
+ * other types -> GPL_ERR_INVALID_TYPE.  A row without a single segment where geo needs one is null. */
 int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, double *out, uint8_t *out_validity, int mem);
-/* row-wise intersects (semantics: spatial_index.rs:102-104 / geo Intersects); Arrow bitmap out */
+/* row-wise intersects (call sites spatial_index.rs:102-123 / geo Intersects); Arrow bitmap out.  Every pair of
+ * Point, MultiPoint, LineString, MultiLineString, Polygon, MultiPolygon arrays; null row -> false */
 int gpl_intersects(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, uint8_t *out_bitmap, int mem);
-/* row-wise contains: polygons[i] contains points[i] (spatial_index.rs:91-96); Arrow bitmap out */
+/* row-wise contains of a point: polygons[i] contains points[i] (spatial_index.rs:91-96); `polygons` may also be a
+ * (Multi)LineString array (spatial_index.rs:125-135: interior of the line, end points only when closed).
+ * Polygon-contains-Polygon (spatial_index.rs:99-101,107-111) is DE-9IM relate in geo and is not provided:
+ * GPL_ERR_INVALID_TYPE.  Arrow bitmap out */
 int gpl_contains(gpl_ctx *ctx, const gpl_array *polygons, const gpl_array *points, uint8_t *out_bitmap, int mem);
 /* secondary trait ops (geoseries.rs:43-83,176-180) */
 int gpl_geom_type(gpl_ctx *ctx, const gpl_array *in, int8_t *out, int mem);

@@ -119,3 +119,39 @@ def convex_hull_vertices(pts: Sequence[Coord]) -> List[Coord]:
             upper.pop()
         upper.append(p)
     return lower[:-1] + upper[:-1]
+
+
+def closed_polygon_has(p: Coord, rings: Sequence[Sequence[Coord]]) -> bool:
+    """p belongs to the closed region: not outside the exterior, not strictly inside a hole"""
+    if not rings or len(rings[0]) == 0:
+        return False
+    if ring_position(p, rings[0]) == 0:
+        return False
+    return all(ring_position(p, h) != 2 for h in rings[1:])
+
+
+def _closed(ring: Sequence[Coord]) -> List[Coord]:
+    r = list(ring)
+    if len(r) >= 2 and tuple(r[0]) != tuple(r[-1]):
+        r.append(r[0])
+    return r
+
+
+def polygons_intersect(a: Sequence[Sequence[Coord]], b: Sequence[Sequence[Coord]]) -> bool:
+    """set definition for VALID polygons (closed regions share a point): some boundary segments meet, or a
+    vertex of one lies in the other's closed region."""
+    ra, rb = [_closed(r) for r in a], [_closed(r) for r in b]
+    if not ra or not rb or len(ra[0]) < 2 or len(rb[0]) < 2:
+        return False
+    for x in ra:
+        for y in rb:
+            if linestrings_intersect(x, y):
+                return True
+    return closed_polygon_has(rb[0][0], ra) or closed_polygon_has(ra[0][0], rb)
+
+
+def linestring_intersects_polygon(ls: Sequence[Coord], rings: Sequence[Sequence[Coord]]) -> bool:
+    rr = [_closed(r) for r in rings]
+    if len(ls) < 2 or not rr:
+        return False
+    return any(linestrings_intersect(ls, r) for r in rr) or closed_polygon_has(ls[0], rr)

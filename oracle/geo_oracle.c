@@ -746,15 +746,207 @@ static int ls_intersects_ls(const double *a, int64_t na, const double *b, int64_
             if (line_intersects_line(b + 2 * j, b + 2 * j + 2, a + 2 * i, a + 2 * i + 2)) return 1;
     return 0;
 }
+/* ---- every type pair: geo 0.27 intersects/{coordinate,line,line_string,polygon,collections}.rs (recalled) ----
+ * Written with geo's own nesting (every vertex tested, the polygon-level bounding-box rejects taken on the
+ * exterior ring exactly where geo takes them); the CUDA kernel uses a shorter but equivalent procedure. */
+typedef struct chain_t { /* linestring, or ring with Polygon::new's closing coord emulated */
+    const double *xy;
+    int64_t n;
+    int closing;
+} chain_t;
+static inline int64_t chain_coords(const chain_t *c) { return c->n + c->closing; }
+static inline const double *chain_at(const chain_t *c, int64_t i) { return c->xy + 2 * (i < c->n ? i : 0); }
+static chain_t mk_line(const double *xy, int64_t c0, int64_t c1) {
+    chain_t c = {xy + 2 * c0, c1 - c0, 0};
+    return c;
+}
+static chain_t mk_ring(const double *xy, int64_t c0, int64_t c1) {
+    chain_t c = {xy + 2 * c0, c1 - c0, 0};
+    if (c.n >= 2) c.closing = !(c.xy[0] == c.xy[2 * (c.n - 1)] && c.xy[1] == c.xy[2 * (c.n - 1) + 1]);
+    return c;
+}
+static int chain_bbox(const chain_t *c, double *b) { return ls_bbox(c->xy, c->n, b); }
+static int bbox_disjoint(int ha, const double *a, int hb, const double *b) {
+    return ha && hb && (a[0] > b[2] || b[0] > a[2] || a[1] > b[3] || b[1] > a[3]);
+}
+/* impl Intersects<Coord> for Polygon: exterior != Outside && all interiors != Inside */
+static int polygon_intersects_coord(const og_array *a, int64_t r0, int64_t r1, const double *p) {
+    const int64_t *ro = a->ring_off;
+    if (r1 <= r0) return 0;
+    if (coord_pos_ring(p[0], p[1], a->xy + 2 * ro[r0], ro[r0 + 1] - ro[r0]) == POS_OUTSIDE) return 0;
+    for (int64_t h = r0 + 1; h < r1; ++h)
+        if (coord_pos_ring(p[0], p[1], a->xy + 2 * ro[h], ro[h + 1] - ro[h]) == POS_INSIDE) return 0;
+    return 1;
+}
+/* blanket impl Intersects<Line> for LineString: bbox reject, then lines().any() */
+static int chain_intersects_line(const chain_t *c, const double *s, const double *e) {
+    double bc[4], bl[4] = {fmin(s[0], e[0]), fmin(s[1], e[1]), fmax(s[0], e[0]), fmax(s[1], e[1])};
+    int hc = chain_bbox(c, bc);
+    if (bbox_disjoint(hc, bc, 1, bl)) return 0;
+    for (int64_t i = 0; i + 1 < chain_coords(c); ++i)
+        if (line_intersects_line(chain_at(c, i), chain_at(c, i + 1), s, e)) return 1;
+    return 0;
+}
+/* impl Intersects<Line> for Polygon */
+static int polygon_intersects_line(const og_array *a, int64_t r0, int64_t r1, const double *s, const double *e) {
+    for (int64_t r = r0; r < r1; ++r) {
+        chain_t ring = mk_ring(a->xy, a->ring_off[r], a->ring_off[r + 1]);
+        if (chain_intersects_line(&ring, s, e)) return 1;
+    }
+    return polygon_intersects_coord(a, r0, r1, s) || polygon_intersects_coord(a, r0, r1, e);
+}
+/* symmetric impl of the blanket LineString impl: has_disjoint_bboxes(linestring, polygon), then lines().any() */
+static int polygon_intersects_chain(const og_array *a, int64_t r0, int64_t r1, const chain_t *c) {
+    if (r1 <= r0) return 0;
+    double bc[4], bp[4];
+    int hc = chain_bbox(c, bc);
+    int hp = ls_bbox(a->xy + 2 * a->ring_off[r0], a->ring_off[r0 + 1] - a->ring_off[r0], bp); /* Polygon::bounding_rect = exterior's */
+    if (bbox_disjoint(hc, bc, hp, bp)) return 0;
+    for (int64_t i = 0; i + 1 < chain_coords(c); ++i)
+        if (polygon_intersects_line(a, r0, r1, chain_at(c, i), chain_at(c, i + 1))) return 1;
+    return 0;
+}
+/* impl Intersects<Polygon> for Polygon: self = (s, s0..s1), polygon = (o, o0..o1) */
+static int polygon_intersects_polygon(const og_array *s, int64_t s0, int64_t s1, const og_array *o, int64_t o0, int64_t o1) {
+    if (s1 <= s0 || o1 <= o0) return 0;
+    double bs[4], bo[4];
+    int hs = ls_bbox(s->xy + 2 * s->ring_off[s0], s->ring_off[s0 + 1] - s->ring_off[s0], bs);
+    int ho = ls_bbox(o->xy + 2 * o->ring_off[o0], o->ring_off[o0 + 1] - o->ring_off[o0], bo);
+    if (bbox_disjoint(hs, bs, ho, bo)) return 0;
+    for (int64_t r = o0; r < o1; ++r) { /* polygon.exterior(), then polygon.interiors() */
+        chain_t ring = mk_ring(o->xy, o->ring_off[r], o->ring_off[r + 1]);
+        if (polygon_intersects_chain(s, s0, s1, &ring)) return 1;
+    }
+    chain_t sext = mk_ring(s->xy, s->ring_off[s0], s->ring_off[s0 + 1]);
+    return polygon_intersects_chain(o, o0, o1, &sext);
+}
+static int geom_class(int t) { return (t == OG_POINT || t == OG_MULTIPOINT) ? 0 : (t == OG_LINESTRING || t == OG_MULTILINESTRING) ? 1 : 2; }
+static void sub_range(const og_array *a, int64_t r, int64_t *lo, int64_t *hi) {
+    if (a->type == OG_POINT) *lo = r, *hi = r + 1;
+    else if (a->type == OG_LINESTRING || a->type == OG_POLYGON) *lo = 0, *hi = 1;
+    else *lo = a->geom_off[r], *hi = a->geom_off[r + 1];
+}
+static chain_t sub_chain(const og_array *a, int64_t r, int64_t k) {
+    if (a->type == OG_LINESTRING) return mk_line(a->xy, a->geom_off[r], a->geom_off[r + 1]);
+    return mk_line(a->xy, a->ring_off[k], a->ring_off[k + 1]);
+}
+static void sub_part(const og_array *a, int64_t r, int64_t q, int64_t *r0, int64_t *r1) {
+    if (a->type == OG_POLYGON) *r0 = a->geom_off[r], *r1 = a->geom_off[r + 1];
+    else *r0 = a->part_off[q], *r1 = a->part_off[q + 1];
+}
+static int row_intersects(const og_array *a, int64_t ra, const og_array *b, int64_t rb) {
+    int ca = geom_class(a->type), cb = geom_class(b->type);
+    int64_t a0, a1, b0, b1;
+    if (ca == 2 && cb == 2) {
+        sub_range(a, ra, &a0, &a1);
+        sub_range(b, rb, &b0, &b1);
+        /* Multi*: self.iter().any(|p| p.intersects(rhs)); Polygon x MultiPolygon is the symmetric impl, so the
+         * MultiPolygon's members are `self` */
+        int self_is_a = b->type == OG_POLYGON;
+        for (int64_t p = a0; p < a1; ++p) {
+            int64_t s0, s1;
+            sub_part(a, ra, p, &s0, &s1);
+            for (int64_t q = b0; q < b1; ++q) {
+                int64_t o0, o1;
+                sub_part(b, rb, q, &o0, &o1);
+                if (self_is_a ? polygon_intersects_polygon(a, s0, s1, b, o0, o1) : polygon_intersects_polygon(b, o0, o1, a, s0, s1)) return 1;
+            }
+        }
+        return 0;
+    }
+    if (ca > cb) {
+        const og_array *t = a; a = b; b = t;
+        int64_t tr = ra; ra = rb; rb = tr;
+        int tc = ca; ca = cb; cb = tc;
+    }
+    sub_range(a, ra, &a0, &a1);
+    sub_range(b, rb, &b0, &b1);
+    if (ca == 0) {
+        for (int64_t i = a0; i < a1; ++i) {
+            const double *p = a->xy + 2 * i;
+            if (cb == 0) {
+                for (int64_t j = b0; j < b1; ++j)
+                    if (b->xy[2 * j] == p[0] && b->xy[2 * j + 1] == p[1]) return 1;
+            } else if (cb == 1) {
+                for (int64_t k = b0; k < b1; ++k) {
+                    chain_t c = sub_chain(b, rb, k);
+                    for (int64_t j = 0; j + 1 < c.n; ++j)
+                        if (line_intersects_coord(c.xy + 2 * j, c.xy + 2 * j + 2, p)) return 1;
+                }
+            } else {
+                for (int64_t q = b0; q < b1; ++q) {
+                    int64_t r0, r1;
+                    sub_part(b, rb, q, &r0, &r1);
+                    if (polygon_intersects_coord(b, r0, r1, p)) return 1;
+                }
+            }
+        }
+        return 0;
+    }
+    for (int64_t k = a0; k < a1; ++k) {
+        chain_t c = sub_chain(a, ra, k);
+        if (cb == 1) {
+            for (int64_t m = b0; m < b1; ++m) {
+                chain_t d = sub_chain(b, rb, m);
+                if (ls_intersects_ls(c.xy, c.n, d.xy, d.n)) return 1;
+            }
+        } else {
+            for (int64_t q = b0; q < b1; ++q) {
+                int64_t r0, r1;
+                sub_part(b, rb, q, &r0, &r1);
+                if (polygon_intersects_chain(b, r0, r1, &c)) return 1;
+            }
+        }
+    }
+    return 0;
+}
 void og_intersects_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads) {
     int nt = resolve_threads(threads);
     (void)nt;
 #pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
     for (int64_t i = 0; i < a->n; ++i) {
         uint8_t r = 0;
-        if (is_valid(a, i) && is_valid(b, i) && a->type == OG_LINESTRING && b->type == OG_LINESTRING) {
-            r = (uint8_t)ls_intersects_ls(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i],
-                                         b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i]);
+        if (is_valid(a, i) && is_valid(b, i)) {
+            if (a->type == OG_LINESTRING && b->type == OG_LINESTRING)
+                r = (uint8_t)ls_intersects_ls(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i],
+                                             b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i]);
+            else
+                r = (uint8_t)row_intersects(a, i, b, i);
+        }
+        out[i] = r;
+    }
+}
+
+/* row-wise contains of a point: (Multi)Polygon -> og_contains_point; (Multi)LineString -> geo 0.27
+ * contains/line_string.rs + contains/line.rs (recalled; spatial_index.rs:125-135 are the call sites) */
+static int line_contains_coord(const double *s, const double *e, const double *c) {
+    if (s[0] == e[0] && s[1] == e[1]) return s[0] == c[0] && s[1] == c[1];
+    return !(c[0] == s[0] && c[1] == s[1]) && !(c[0] == e[0] && c[1] == e[1]) && line_intersects_coord(s, e, c);
+}
+static int linestring_contains_coord(const double *xy, int64_t n, const double *c) {
+    if (n == 0) return 0;
+    const double *f = xy, *l = xy + 2 * (n - 1);
+    if ((c[0] == f[0] && c[1] == f[1]) || (c[0] == l[0] && c[1] == l[1])) return f[0] == l[0] && f[1] == l[1]; /* is_closed() */
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const double *s = xy + 2 * i, *e = xy + 2 * i + 2;
+        if (line_contains_coord(s, e, c) || (i > 0 && c[0] == s[0] && c[1] == s[1])) return 1;
+    }
+    return 0;
+}
+void og_contains_rowwise(const og_array *a, const double *pts_xy, const uint8_t *pts_valid, uint8_t *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
+    for (int64_t i = 0; i < a->n; ++i) {
+        uint8_t r = 0;
+        int pv = pts_valid ? ((pts_valid[i >> 3] >> (i & 7)) & 1) : 1;
+        if (is_valid(a, i) && pv) {
+            const double *p = pts_xy + 2 * i;
+            if (a->type == OG_POLYGON || a->type == OG_MULTIPOLYGON) r = (uint8_t)og_contains_point(a, i, p[0], p[1]);
+            else if (a->type == OG_LINESTRING) r = (uint8_t)linestring_contains_coord(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i], p);
+            else if (a->type == OG_MULTILINESTRING)
+                for (int64_t k = a->geom_off[i]; k < a->geom_off[i + 1] && !r; ++k)
+                    r = (uint8_t)linestring_contains_coord(a->xy + 2 * a->ring_off[k], a->ring_off[k + 1] - a->ring_off[k], p);
         }
         out[i] = r;
     }
@@ -839,13 +1031,74 @@ static double point_polygon_distance(const double *p, const og_array *a, int64_t
     for (int64_t k = 0; k + 1 < ro[r0 + 1] - ro[r0]; ++k) ext = fmin(ext, line_segment_distance(p, xy + 2 * k, xy + 2 * k + 2));
     return fmin(acc, ext);
 }
+/* nearest_neighbour_distance(a, b): min over {point of a -> lines of b} U {point of b -> lines of a}; geo finds
+ * the nearest line through an rstar tree and evaluates the same point-line formula */
+static double chain_nn_distance(const chain_t *a, const chain_t *b) {
+    double m = 1.7976931348623157e308;
+    int64_t na = chain_coords(a), nb = chain_coords(b);
+    for (int64_t j = 0; j < nb; ++j)
+        for (int64_t i = 0; i + 1 < na; ++i) m = fmin(m, line_segment_distance(chain_at(b, j), chain_at(a, i), chain_at(a, i + 1)));
+    for (int64_t i = 0; i < na; ++i)
+        for (int64_t j = 0; j + 1 < nb; ++j) m = fmin(m, line_segment_distance(chain_at(a, i), chain_at(b, j), chain_at(b, j + 1)));
+    return m;
+}
+/* ring_contains_point: strictly inside the exterior ring */
+static int exterior_contains(const og_array *p, int64_t r0, const double *c) {
+    return coord_pos_ring(c[0], c[1], p->xy + 2 * p->ring_off[r0], p->ring_off[r0 + 1] - p->ring_off[r0]) == POS_INSIDE;
+}
+/* impl EuclideanDistance<Polygon> for LineString (geo 0.27 euclidean_distance.rs, recalled) */
+static double ls_polygon_distance(const chain_t *ls, const og_array *p, int64_t i, int *ok) {
+    int64_t r0 = p->geom_off[i], r1 = p->geom_off[i + 1];
+    if (ls->n < 2 || r1 <= r0 || p->ring_off[r0 + 1] - p->ring_off[r0] < 2) { /* empty rstar tree -> unwrap() panics */
+        *ok = 0;
+        return NAN;
+    }
+    if (polygon_intersects_chain(p, r0, r1, ls)) return 0.0;
+    if (r1 - r0 > 1 && exterior_contains(p, r0, ls->xy)) {
+        double m = 1.7976931348623157e308;
+        for (int64_t r = r0 + 1; r < r1; ++r) {
+            chain_t ring = mk_ring(p->xy, p->ring_off[r], p->ring_off[r + 1]);
+            m = fmin(m, chain_nn_distance(ls, &ring));
+        }
+        return m;
+    }
+    chain_t ext = mk_ring(p->xy, p->ring_off[r0], p->ring_off[r0 + 1]);
+    return chain_nn_distance(ls, &ext);
+}
+/* impl EuclideanDistance<Polygon> for Polygon.  geo switches to rotating calipers (min_poly_dist) when both
+ * polygons are convex; that path computes the same minimum with different roundings and is restated here by
+ * the nearest-neighbour form (tolerance 1e-9 relative covers it). */
+static double polygon_polygon_distance(const og_array *a, int64_t ia, const og_array *b, int64_t ib, int *ok) {
+    int64_t a0 = a->geom_off[ia], a1 = a->geom_off[ia + 1], b0 = b->geom_off[ib], b1 = b->geom_off[ib + 1];
+    if (a1 <= a0 || b1 <= b0 || a->ring_off[a0 + 1] - a->ring_off[a0] < 2 || b->ring_off[b0 + 1] - b->ring_off[b0] < 2) {
+        *ok = 0;
+        return NAN;
+    }
+    if (polygon_intersects_polygon(a, a0, a1, b, b0, b1)) return 0.0;
+    chain_t ea = mk_ring(a->xy, a->ring_off[a0], a->ring_off[a0 + 1]), eb = mk_ring(b->xy, b->ring_off[b0], b->ring_off[b0 + 1]);
+    if (a1 - a0 > 1 && exterior_contains(a, a0, eb.xy)) {
+        double m = 1.7976931348623157e308;
+        for (int64_t r = a0 + 1; r < a1; ++r) {
+            chain_t ring = mk_ring(a->xy, a->ring_off[r], a->ring_off[r + 1]);
+            m = fmin(m, chain_nn_distance(&eb, &ring));
+        }
+        return m;
+    }
+    if (b1 - b0 > 1 && exterior_contains(b, b0, ea.xy)) {
+        double m = 1.7976931348623157e308;
+        for (int64_t r = b0 + 1; r < b1; ++r) {
+            chain_t ring = mk_ring(b->xy, b->ring_off[r], b->ring_off[r + 1]);
+            m = fmin(m, chain_nn_distance(&ea, &ring));
+        }
+        return m;
+    }
+    return chain_nn_distance(&ea, &eb);
+}
 int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int threads) {
     int nt = resolve_threads(threads);
     (void)nt;
     int ta = a->type, tb = b->type;
-    int supported = (ta == OG_POINT || ta == OG_LINESTRING || ta == OG_POLYGON) &&
-                    (tb == OG_POINT || tb == OG_LINESTRING || tb == OG_POLYGON) &&
-                    !(ta == OG_POLYGON && tb != OG_POINT) && !(tb == OG_POLYGON && ta != OG_POINT);
+    int supported = (ta == OG_POINT || ta == OG_LINESTRING || ta == OG_POLYGON) && (tb == OG_POINT || tb == OG_LINESTRING || tb == OG_POLYGON);
     if (!supported || a->n != b->n) return -1;
 #pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
     for (int64_t i = 0; i < a->n; ++i) {
@@ -862,6 +1115,14 @@ int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int t
                                    b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i], &ok);
             else if (ta == OG_POINT && tb == OG_POLYGON) v = point_polygon_distance(a->xy + 2 * i, b, i);
             else if (ta == OG_POLYGON && tb == OG_POINT) v = point_polygon_distance(b->xy + 2 * i, a, i);
+            else if (ta == OG_LINESTRING && tb == OG_POLYGON) {
+                chain_t ls = mk_line(a->xy, a->geom_off[i], a->geom_off[i + 1]);
+                v = ls_polygon_distance(&ls, b, i, &ok);
+            } else if (ta == OG_POLYGON && tb == OG_LINESTRING) {
+                chain_t ls = mk_line(b->xy, b->geom_off[i], b->geom_off[i + 1]);
+                v = ls_polygon_distance(&ls, a, i, &ok);
+            } else
+                v = polygon_polygon_distance(a, i, b, i, &ok);
             (void)ok;
         }
         out[i] = v;

@@ -83,8 +83,11 @@ int og_contains_point(const og_array *polys, int64_t i, double px, double py);
 void og_contains_join(const og_array *polys, const double *pts_xy, int64_t n_pts, int32_t *first_id,
                       int32_t *count, int use_grid, int threads);
 
-/* row-wise LineString x LineString intersects (geo Intersects) -> 0/1 bytes */
+/* row-wise intersects for every pair of Point / MultiPoint / LineString / MultiLineString / Polygon /
+ * MultiPolygon arrays (geo Intersects; spatial_index.rs:102-123 call sites) -> 0/1 bytes */
 void og_intersects_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads);
+/* row-wise `a[i] contains point i` for (Multi)Polygon and (Multi)LineString rows (spatial_index.rs:91-96,125-135) */
+void og_contains_rowwise(const og_array *a, const double *pts_xy, const uint8_t *pts_valid, uint8_t *out, int threads);
 /* row-wise euclidean distance (geo EuclideanDistance) for Point/LineString/Polygon pairs */
 int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int threads);
 

@@ -194,6 +194,15 @@ def intersects_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
     return out.astype(bool)
 
 
+def contains_rowwise(a: OGArray, pts_xy: np.ndarray, threads: int = 1) -> np.ndarray:
+    """a[i] contains point i — (Multi)Polygon or (Multi)LineString rows"""
+    sa, ka = a._c()
+    pts = np.ascontiguousarray(pts_xy, dtype=np.float64)
+    out = np.empty(len(a), dtype=np.uint8)
+    lib().og_contains_rowwise(C.byref(sa), _p(pts), None, _p(out), C.c_int(threads))
+    return out.astype(bool)
+
+
 def distance_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
     sa, ka = a._c()
     sb, kb = b._c()

@@ -160,3 +160,59 @@ def test_synth_generators_are_bit_reproducible(og):
     assert xy.shape == (50 * 65, 2) and np.array_equal(xy[ro[:-1]], xy[ro[1:] - 1])
     a = og.area(og.OGArray(og.POLYGON, xy, geom_off=go, ring_off=ro))
     assert (a > 10).all() and (a < 80).all()
+
+
+def test_generic_intersects_against_exact_referee_and_symmetry(og, conv):
+    """the all-type-pairs restatement of geo's Intersects: polygon pairs and linestring x polygon agree with
+    the exact-rational set definition, every type pair is symmetric in its arguments"""
+    import shapes
+    from oracle import exact
+    from geopolars_b200 import GeoArrowArray, GeometryType
+
+    T = dict(zip(shapes.KINDS, [GeometryType.POINT, GeometryType.MULTIPOINT, GeometryType.LINESTRING,
+                                GeometryType.MULTILINESTRING, GeometryType.POLYGON, GeometryType.MULTIPOLYGON]))
+    rng = np.random.default_rng(1)
+    A, B = shapes.random_rows(rng, "polygon", 400), shapes.random_rows(rng, "polygon", 400)
+    L = shapes.random_rows(rng, "linestring", 400)
+    ga, gb, gl = (GeoArrowArray.from_shapes(T[k], r) for k, r in (("polygon", A), ("polygon", B), ("linestring", L)))
+    got = og.intersects_rowwise(conv(ga), conv(gb))
+    assert np.array_equal(got, [exact.polygons_intersect(a, b) for a, b in zip(A, B)]) and got.any() and not got.all()
+    got = og.intersects_rowwise(conv(gl), conv(gb))
+    assert np.array_equal(got, [exact.linestring_intersects_polygon(l, b) for l, b in zip(L, B)]) and got.any()
+    for ka in shapes.KINDS:
+        for kb in shapes.KINDS:
+            rb = shapes.random_rows(rng, kb, 120)
+            ra = shapes.plant_touching(rng, ka, shapes.random_rows(rng, ka, 120), kb, rb)
+            x, y = GeoArrowArray.from_shapes(T[ka], ra), GeoArrowArray.from_shapes(T[kb], rb)
+            ab, ba = og.intersects_rowwise(conv(x), conv(y)), og.intersects_rowwise(conv(y), conv(x))
+            assert np.array_equal(ab, ba), (ka, kb)
+            assert ab.any(), (ka, kb)
+
+
+def test_linestring_contains_point_known_answers(og, conv):
+    from geopolars_b200 import GeoArrowArray, GeometryType
+
+    L = [[(0, 0), (2, 0), (2, 2), (0, 0)], [(0, 0), (2, 0), (2, 2)], [(0, 0), (2, 0), (2, 2)], [(0, 0), (2, 0), (2, 2)],
+         [(1, 1), (1, 1)], [], [(0, 0), (4, 4)], [(0, 0), (4, 4)]]
+    P = [(0, 0), (0, 0), (2, 0), (1, 0), (1, 1), (1, 1), (1, 1), (1, 1.5)]
+    got = og.contains_rowwise(conv(GeoArrowArray.from_shapes(GeometryType.LINESTRING, L)), np.array(P, float))
+    #      closed end  open end  vertex  on segment  degenerate (is_closed)  empty  interior  off
+    assert got.tolist() == [True, False, True, True, True, False, True, False]
+
+
+def test_polygon_linestring_distance_known_answers(og, conv):
+    from geopolars_b200 import GeoArrowArray, GeometryType
+
+    sq = [(0, 0), (10, 0), (10, 10), (0, 10), (0, 0)]
+    hole = [(2, 2), (2, 8), (8, 8), (8, 2), (2, 2)]
+    inner = [(4, 4), (6, 4), (6, 6), (4, 6), (4, 4)]
+    right = [(13, 0), (15, 0), (15, 10), (13, 10), (13, 0)]
+    diag = [(13, 14), (20, 14), (20, 20), (13, 14)]
+    A = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[sq], [sq], [sq, hole], [sq, hole], [sq]])
+    B = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[right], [diag], [inner], [right], [inner]])
+    d = og.distance_rowwise(conv(A), conv(B))
+    assert d.tolist() == [3.0, 5.0, 2.0, 3.0, 0.0]
+    assert og.distance_rowwise(conv(B), conv(A)).tolist() == d.tolist()
+    L = GeoArrowArray.from_shapes(GeometryType.LINESTRING, [[(13, 5), (20, 5)], [(13, 14), (20, 20)], [(4, 5), (6, 5)], [(5, 5), (12, 5)], [(1, 1), (2, 1)]])
+    assert og.distance_rowwise(conv(A), conv(L)).tolist() == [3.0, 5.0, 2.0, 0.0, 0.0]
+    assert og.distance_rowwise(conv(L), conv(A)).tolist() == [3.0, 5.0, 2.0, 0.0, 0.0]
