@@ -105,6 +105,8 @@ SIGNATURES = {
     "gpl_array_free": (None, [_P]),
     "gpl_array_from_wkb": (_INT, [_P, _P, _P, _P, _I64, C.POINTER(_P)]),
     "gpl_array_to_wkb": (_INT, [_P, _P, _P, _P, C.POINTER(_I64)]),
+    "gpl_wkb_decode": (_INT, [_P, _P, _P, _INT, _P, _I64, _INT, C.POINTER(_P)]),
+    "gpl_wkb_encode": (_INT, [_P, _P, _P, _INT, _P, C.POINTER(_I64), _INT]),
     "gpl_array_import_arrow": (_INT, [_P, _P, _P, C.POINTER(_P)]),
     "gpl_array_export_arrow": (_INT, [_P, _P, _P, _P]),
     "gpl_export_f64_arrow": (_INT, [_P, _P, _I64, _P, _P]),

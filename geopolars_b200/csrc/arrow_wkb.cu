@@ -1,10 +1,7 @@
-// arrow_wkb.cu — host-side data formats either side of the hot path:
-//   * WKB <-> GeoArrow, decoded ONCE per column (the reference re-parses WKB into geo structs on every
-//     op: geopolars/geopolars-geo/src/util.rs:27-37 `iter_geom`, :11-24 `from_geom_vec`; README.md:83),
-//   * Arrow C Data Interface import/export, the same structs the reference moves across its own FFI
-//     (py-geopolars/src/ffi.rs:14-49).
-// Pure host C++ (compiled by nvcc for convenience); the device work is the single H2D/D2H copy done by
-// gpl_array_from_buffers / gpl_array_copy_out.
+// arrow_wkb.cu — Arrow C Data Interface import/export, the same structs the reference moves across its own
+// FFI (py-geopolars/src/ffi.rs:14-49).  geoarrow nested layouts are re-based on the host and uploaded with one
+// H2D copy per buffer; WKB `binary` / `large_binary` columns are handed to the GPU codec (k_wkb.cu).
+// Pure host C++ (compiled by nvcc for convenience).
 #include <stdlib.h>
 #include <string.h>
 
@@ -67,221 +64,13 @@ static int upload(gpl_ctx *ctx, const HostGeo &h, gpl_array **out) {
     return gpl_array_from_buffers(ctx, &b, out);
 }
 
-// ---- WKB reader --------------------------------------------------------------------------------------
-struct Rd {
-    const uint8_t *p, *end;
-    bool le = true;
-    bool ok = true;
-    bool need(size_t n) {
-        if ((size_t)(end - p) < n) ok = false;
-        return ok;
-    }
-    uint8_t u8() {
-        if (!need(1)) return 0;
-        return *p++;
-    }
-    uint32_t u32() {
-        if (!need(4)) return 0;
-        uint32_t v;
-        if (le) v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-        else v = (uint32_t)p[3] | ((uint32_t)p[2] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[0] << 24);
-        p += 4;
-        return v;
-    }
-    double f64() {
-        if (!need(8)) return 0;
-        uint64_t v = 0;
-        if (le) for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
-        else for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
-        p += 8;
-        double d;
-        memcpy(&d, &v, 8);
-        return d;
-    }
-    // geometry header: byte order + type (ISO codes 1..6; EWKB SRID flag tolerated; Z/M rejected)
-    int header() {
-        uint8_t bo = u8();
-        le = bo != 0;
-        uint32_t t = u32();
-        if (t & 0x20000000u) (void)u32();  // EWKB SRID
-        if (t & 0xC0000000u) return -1;    // EWKB Z/M
-        t &= 0x0fffffffu;
-        if (t >= 1000) return -1;          // ISO Z/M/ZM
-        return (int)t;
-    }
-};
-
-static int wkb_to_code(int t) {  // WKB type -> reference GeometryType code
-    switch (t) {
-    case 1: return GPL_POINT;
-    case 2: return GPL_LINESTRING;
-    case 3: return GPL_POLYGON;
-    case 4: return GPL_MULTIPOINT;
-    case 5: return GPL_MULTILINESTRING;
-    case 6: return GPL_MULTIPOLYGON;
-    default: return GPL_MISSING;
-    }
-}
+static int fetch(gpl_ctx *ctx, const gpl_array *a, HostGeo &h);
 
 }  // namespace gpl
 
 using namespace gpl;
 
-extern "C" int gpl_array_from_wkb(gpl_ctx *ctx, const uint8_t *bytes, const int32_t *offsets, const uint8_t *validity, int64_t n,
-                                  gpl_array **out) {
-    GPL_REQUIRE(ctx && out && (n == 0 || (bytes && offsets)), GPL_ERR_INVALID_ARG, "gpl_array_from_wkb: NULL argument");
-    // pass 1: which geometry types occur
-    bool seen[8] = {false};
-    for (int64_t i = 0; i < n; ++i) {
-        if (validity && !((validity[i >> 3] >> (i & 7)) & 1)) continue;
-        if (offsets[i + 1] - offsets[i] < 5) continue;
-        Rd r{bytes + offsets[i], bytes + offsets[i + 1]};
-        int t = r.header();
-        int code = t > 0 ? wkb_to_code(t) : GPL_MISSING;
-        GPL_REQUIRE(r.ok && code != GPL_MISSING, GPL_ERR_UNSUPPORTED, "row %lld: unsupported WKB geometry type (XY Point..MultiPolygon only)",
-                    (long long)i);
-        seen[code] = true;
-    }
-    int target = GPL_POINT;
-    {
-        bool pt = seen[GPL_POINT] || seen[GPL_MULTIPOINT], ls = seen[GPL_LINESTRING] || seen[GPL_MULTILINESTRING],
-             pg = seen[GPL_POLYGON] || seen[GPL_MULTIPOLYGON];
-        GPL_REQUIRE((int)pt + (int)ls + (int)pg <= 1, GPL_ERR_INVALID_TYPE,
-                    "Expected a single geometry family per column (found a mix of point/line/polygon rows)");
-        if (pg) target = seen[GPL_MULTIPOLYGON] ? GPL_MULTIPOLYGON : GPL_POLYGON;
-        else if (ls) target = seen[GPL_MULTILINESTRING] ? GPL_MULTILINESTRING : GPL_LINESTRING;
-        else target = seen[GPL_MULTIPOINT] ? GPL_MULTIPOINT : GPL_POINT;
-    }
-    HostGeo h;
-    h.type = target;
-    h.n = n;
-    const bool has_geom = target != GPL_POINT;
-    const bool has_ring = target == GPL_POLYGON || target == GPL_MULTILINESTRING || target == GPL_MULTIPOLYGON;
-    const bool has_part = target == GPL_MULTIPOLYGON;
-    if (has_geom) h.geom.push_back(0);
-    if (has_ring) h.ring.push_back(0);
-    if (has_part) h.part.push_back(0);
-    bool any_null = false;
-    std::vector<uint8_t> valid((size_t)(n + 7) / 8, 0);
-    const double qnan = __builtin_nan("");
-    auto coords = [&](Rd &r, uint32_t cnt) {
-        for (uint32_t k = 0; k < cnt && r.ok; ++k) {
-            double x = r.f64(), y = r.f64();
-            h.xy.push_back(x);
-            h.xy.push_back(y);
-        }
-    };
-    auto polygon_body = [&](Rd &r) {  // rings of one polygon -> ring offsets
-        uint32_t nr = r.u32();
-        for (uint32_t k = 0; k < nr && r.ok; ++k) {
-            coords(r, r.u32());
-            h.ring.push_back((int64_t)h.xy.size() / 2);
-        }
-    };
-    for (int64_t i = 0; i < n; ++i) {
-        bool isnull = (validity && !((validity[i >> 3] >> (i & 7)) & 1)) || offsets[i + 1] - offsets[i] < 5;
-        if (!isnull) {
-            Rd r{bytes + offsets[i], bytes + offsets[i + 1]};
-            int t = r.header();
-            switch (t) {
-            case 1: {
-                double x = r.f64(), y = r.f64();
-                h.xy.push_back(x);
-                h.xy.push_back(y);
-                break;
-            }
-            case 2:
-                coords(r, r.u32());
-                if (target == GPL_MULTILINESTRING) h.ring.push_back((int64_t)h.xy.size() / 2);
-                break;
-            case 3:
-                polygon_body(r);
-                if (has_part) h.part.push_back((int64_t)h.ring.size() - 1);
-                break;
-            case 4: {
-                uint32_t np = r.u32();
-                for (uint32_t k = 0; k < np && r.ok; ++k) {
-                    Rd s{r.p, r.end};
-                    int st = s.header();
-                    if (st != 1) r.ok = false;
-                    double x = s.f64(), y = s.f64();
-                    h.xy.push_back(x);
-                    h.xy.push_back(y);
-                    r.p = s.p;
-                    r.ok = r.ok && s.ok;
-                }
-                break;
-            }
-            case 5: {
-                uint32_t nl = r.u32();
-                for (uint32_t k = 0; k < nl && r.ok; ++k) {
-                    Rd s{r.p, r.end};
-                    int st = s.header();
-                    if (st != 2) r.ok = false;
-                    coords(s, s.u32());
-                    h.ring.push_back((int64_t)h.xy.size() / 2);
-                    r.p = s.p;
-                    r.ok = r.ok && s.ok;
-                }
-                break;
-            }
-            case 6: {
-                uint32_t npoly = r.u32();
-                for (uint32_t k = 0; k < npoly && r.ok; ++k) {
-                    Rd s{r.p, r.end};
-                    int st = s.header();
-                    if (st != 3) r.ok = false;
-                    polygon_body(s);
-                    h.part.push_back((int64_t)h.ring.size() - 1);
-                    r.p = s.p;
-                    r.ok = r.ok && s.ok;
-                }
-                break;
-            }
-            default:
-                r.ok = false;
-            }
-            GPL_REQUIRE(r.ok, GPL_ERR_INVALID_ARG, "row %lld: truncated or malformed WKB", (long long)i);
-            valid[i >> 3] |= (uint8_t)(1u << (i & 7));
-        } else {
-            any_null = true;
-            if (target == GPL_POINT) {
-                h.xy.push_back(qnan);
-                h.xy.push_back(qnan);
-            }
-        }
-        // close this row at every level
-        if (target == GPL_POINT) continue;
-        if (target == GPL_LINESTRING || target == GPL_MULTIPOINT) h.geom.push_back((int64_t)h.xy.size() / 2);
-        else if (target == GPL_POLYGON || target == GPL_MULTILINESTRING) h.geom.push_back((int64_t)h.ring.size() - 1);
-        else h.geom.push_back((int64_t)h.part.size() - 1);
-    }
-    if (any_null) h.valid = valid;
-    return upload(ctx, h, out);
-}
-
-// ---- WKB writer --------------------------------------------------------------------------------------
 namespace gpl {
-struct Wr {
-    uint8_t *p;  // nullptr: size only
-    int64_t n = 0;
-    void u8(uint8_t v) {
-        if (p) p[n] = v;
-        n += 1;
-    }
-    void u32(uint32_t v) {
-        if (p) memcpy(p + n, &v, 4);
-        n += 4;
-    }
-    void f64(double v) {
-        if (p) memcpy(p + n, &v, 8);
-        n += 8;
-    }
-    void head(uint32_t t) {
-        u8(1);
-        u32(t);
-    }
-};
 static int fetch(gpl_ctx *ctx, const gpl_array *a, HostGeo &h) {
     h.type = a->type;
     h.n = a->n_geoms;
@@ -293,78 +82,7 @@ static int fetch(gpl_ctx *ctx, const gpl_array *a, HostGeo &h) {
     return gpl_array_copy_out(ctx, a, h.xy.data(), h.geom.empty() ? nullptr : h.geom.data(), h.part.empty() ? nullptr : h.part.data(),
                               h.ring.empty() ? nullptr : h.ring.data(), h.valid.empty() ? nullptr : h.valid.data(), GPL_HOST);
 }
-static void write_row(const HostGeo &h, int64_t i, Wr &w) {
-    auto pt = [&](int64_t c) {
-        w.f64(h.xy[2 * c]);
-        w.f64(h.xy[2 * c + 1]);
-    };
-    auto line = [&](int64_t c0, int64_t c1) {
-        w.u32((uint32_t)(c1 - c0));
-        for (int64_t c = c0; c < c1; ++c) pt(c);
-    };
-    auto poly = [&](int64_t r0, int64_t r1) {
-        w.u32((uint32_t)(r1 - r0));
-        for (int64_t r = r0; r < r1; ++r) line(h.ring[r], h.ring[r + 1]);
-    };
-    switch (h.type) {
-    case GPL_POINT:
-        w.head(1);
-        pt(i);
-        break;
-    case GPL_LINESTRING:
-        w.head(2);
-        line(h.geom[i], h.geom[i + 1]);
-        break;
-    case GPL_POLYGON:
-        w.head(3);
-        poly(h.geom[i], h.geom[i + 1]);
-        break;
-    case GPL_MULTIPOINT:
-        w.head(4);
-        w.u32((uint32_t)(h.geom[i + 1] - h.geom[i]));
-        for (int64_t c = h.geom[i]; c < h.geom[i + 1]; ++c) {
-            w.head(1);
-            pt(c);
-        }
-        break;
-    case GPL_MULTILINESTRING:
-        w.head(5);
-        w.u32((uint32_t)(h.geom[i + 1] - h.geom[i]));
-        for (int64_t l = h.geom[i]; l < h.geom[i + 1]; ++l) {
-            w.head(2);
-            line(h.ring[l], h.ring[l + 1]);
-        }
-        break;
-    case GPL_MULTIPOLYGON:
-        w.head(6);
-        w.u32((uint32_t)(h.geom[i + 1] - h.geom[i]));
-        for (int64_t q = h.geom[i]; q < h.geom[i + 1]; ++q) {
-            w.head(3);
-            poly(h.part[q], h.part[q + 1]);
-        }
-        break;
-    default:
-        break;
-    }
-}
 }  // namespace gpl
-
-extern "C" int gpl_array_to_wkb(gpl_ctx *ctx, const gpl_array *a, int32_t *offsets, uint8_t *bytes, int64_t *n_bytes) {
-    GPL_REQUIRE(ctx && a && offsets && n_bytes, GPL_ERR_INVALID_ARG, "gpl_array_to_wkb: NULL argument");
-    HostGeo h;
-    GPL_TRY(fetch(ctx, a, h));
-    Wr w{bytes};
-    for (int64_t i = 0; i < h.n; ++i) {
-        offsets[i] = (int32_t)w.n;
-        bool valid = h.valid.empty() || ((h.valid[i >> 3] >> (i & 7)) & 1);
-        if (valid) write_row(h, i, w);
-        GPL_REQUIRE(w.n < (1LL << 31), GPL_ERR_UNSUPPORTED, "WKB column exceeds 2 GiB (int32 offsets)");
-    }
-    offsets[h.n] = (int32_t)w.n;
-    if (bytes) GPL_REQUIRE(*n_bytes >= w.n, GPL_ERR_INVALID_ARG, "WKB buffer too small: need %lld bytes", (long long)w.n);
-    *n_bytes = w.n;
-    return GPL_OK;
-}
 
 // ---- Arrow C Data Interface: import ------------------------------------------------------------------
 namespace gpl {
@@ -448,20 +166,13 @@ extern "C" int gpl_array_import_arrow(gpl_ctx *ctx, const void *array, const voi
             if (bit(bm, a->offset + i)) valid[i >> 3] |= (uint8_t)(1u << (i & 7));
     }
     // WKB column ("z" binary / "Z" large binary): what every bundled fixture of the reference holds
+    // (decoded on the GPU: k_wkb.cu)
     if (strcmp(s->format, "z") == 0 || strcmp(s->format, "Z") == 0) {
         const uint8_t *data = static_cast<const uint8_t *>(a->buffers[2]);
-        std::vector<int32_t> off((size_t)n + 1);
-        if (s->format[0] == 'z') {
-            const int32_t *o = static_cast<const int32_t *>(a->buffers[1]) + a->offset;
-            for (int64_t i = 0; i <= n; ++i) off[i] = o[i] - o[0];
-            data += o[0];
-        } else {
-            const int64_t *o = static_cast<const int64_t *>(a->buffers[1]) + a->offset;
-            GPL_REQUIRE(o[n] - o[0] < (1LL << 31), GPL_ERR_UNSUPPORTED, "large_binary WKB column above 2 GiB");
-            for (int64_t i = 0; i <= n; ++i) off[i] = (int32_t)(o[i] - o[0]);
-            data += o[0];
-        }
-        return gpl_array_from_wkb(ctx, data, off.data(), valid.empty() ? nullptr : valid.data(), n, out);
+        const bool wide = s->format[0] == 'Z';
+        const void *o = wide ? static_cast<const void *>(static_cast<const int64_t *>(a->buffers[1]) + a->offset)
+                             : static_cast<const void *>(static_cast<const int32_t *>(a->buffers[1]) + a->offset);
+        return gpl_wkb_decode(ctx, data, o, wide ? 64 : 32, valid.empty() ? nullptr : valid.data(), n, GPL_HOST, out);
     }
     // geoarrow nested layouts: walk the list levels down to the coordinate array
     const ArrowSchema *ls[3];

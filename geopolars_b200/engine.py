@@ -155,6 +155,26 @@ class Context:
             wkb = pa.array(list(wkb), type=pa.binary())
         return self.import_arrow(wkb)
 
+    def decode_wkb(self, data, offsets, valid=None, n=None, offset_width=None, device=False) -> "DeviceArray":
+        """WKB column -> GeoArrow on the GPU (gpl_wkb_decode).  Host form: numpy `data` (uint8), `offsets`
+        (int32 / int64, need not start at 0), `valid` (bool array or None).  Device form (`device=True`):
+        `data`, `offsets`, `valid` are raw device addresses (ints; `valid` = Arrow bitmap), `n` rows,
+        `offset_width` 32 | 64 — e.g. torch tensors' data_ptr()."""
+        h = C.c_void_p()
+        if device:
+            check(self.lib.gpl_wkb_decode(self._h, C.c_void_p(data), C.c_void_p(offsets), int(offset_width),
+                                          C.c_void_p(valid) if valid else None, int(n), GPL_DEVICE, C.byref(h)))
+            return DeviceArray(self, h)
+        offsets = np.ascontiguousarray(offsets)
+        if offsets.dtype not in (np.int32, np.int64):
+            offsets = offsets.astype(np.int64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        n = len(offsets) - 1
+        bm = None if valid is None else np.packbits(np.asarray(valid, dtype=bool), bitorder="little")
+        check(self.lib.gpl_wkb_decode(self._h, _np_ptr(data) if data.size else None, _np_ptr(offsets), 32 if offsets.dtype == np.int32 else 64,
+                                      None if bm is None else _np_ptr(bm), n, GPL_HOST, C.byref(h)))
+        return DeviceArray(self, h)
+
     def __del__(self):
         try:
             self.close()
@@ -221,6 +241,23 @@ class DeviceArray:
         host = self.to_host()
         validity = None if host.valid is None else pa.py_buffer(np.packbits(host.valid, bitorder="little").tobytes())
         return pa.Array.from_buffers(pa.binary(), n, [validity, pa.py_buffer(off.tobytes()), pa.py_buffer(buf[: nbytes.value].tobytes())])
+
+    def encode_wkb(self, offset_width: int = 32, device_out=None):
+        """GeoArrow -> WKB on the GPU (gpl_wkb_encode).  Returns (offsets, bytes) as numpy arrays; with
+        `device_out=(offsets_ptr, bytes_ptr, capacity)` writes into device memory and returns the byte count."""
+        n = len(self)
+        nbytes = C.c_int64(0)
+        lib, cx = self.ctx.lib, self.ctx._h
+        if device_out is not None:
+            optr, bptr, cap = device_out
+            nbytes.value = int(cap)
+            check(lib.gpl_wkb_encode(cx, self._h, C.c_void_p(optr), offset_width, C.c_void_p(bptr), C.byref(nbytes), GPL_DEVICE))
+            return nbytes.value
+        off = np.zeros(n + 1, dtype=np.int32 if offset_width == 32 else np.int64)
+        check(lib.gpl_wkb_encode(cx, self._h, _np_ptr(off), offset_width, None, C.byref(nbytes), GPL_HOST))
+        buf = np.empty(max(nbytes.value, 1), dtype=np.uint8)
+        check(lib.gpl_wkb_encode(cx, self._h, _np_ptr(off), offset_width, _np_ptr(buf), C.byref(nbytes), GPL_HOST))
+        return off, buf[: nbytes.value]
 
     def free(self) -> None:
         if getattr(self, "_h", None) and self.ctx._h:

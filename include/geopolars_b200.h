@@ -148,6 +148,15 @@ int gpl_array_from_wkb(gpl_ctx *ctx, const uint8_t *bytes, const int32_t *offset
 /* GeoArrow -> WKB (from_geom_vec, util.rs:11-24). Two calls: first with bytes == NULL to get
  * *n_bytes and offsets, then with a buffer of that size. Host output. */
 int gpl_array_to_wkb(gpl_ctx *ctx, const gpl_array *a, int32_t *offsets, uint8_t *bytes, int64_t *n_bytes);
+/* The codec itself, on the GPU (util.rs:11-37 is the per-row, per-op host loop it replaces): bytes / offsets /
+ * validity in host OR device memory (`mem`), offsets int32 (`binary`) or int64 (`large_binary`) per
+ * `offset_width`; offsets need not start at 0 (sliced arrays).  gpl_wkb_encode follows the two-call protocol
+ * of gpl_array_to_wkb (bytes == NULL: offsets and *n_bytes only) and writes little-endian ISO WKB; null rows
+ * are zero-length.  gpl_array_from_wkb / gpl_array_to_wkb are the (host, int32) forms of these. */
+int gpl_wkb_decode(gpl_ctx *ctx, const uint8_t *bytes, const void *offsets, int offset_width, const uint8_t *validity,
+                   int64_t n, int mem, gpl_array **out);
+int gpl_wkb_encode(gpl_ctx *ctx, const gpl_array *a, void *offsets, int offset_width, uint8_t *bytes, int64_t *n_bytes,
+                   int mem);
 
 /* Arrow C Data Interface (same structs the reference moves across its FFI, py-geopolars/src/ffi.rs:14-49).
  * Accepts geoarrow nested layouts (interleaved or struct coords, List or LargeList) and WKB

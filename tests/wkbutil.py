@@ -48,3 +48,47 @@ def column_to_shapes(offsets: np.ndarray, data: np.ndarray):
     assert len(types) == 1, types
     t = types.pop()
     return code[t], [g for _, g in rows]
+
+
+def dump(wkb_type: int, shape, big_endian: bool = False, srid=None) -> bytes:
+    """nested python lists -> ISO WKB (optionally big endian / with the EWKB SRID flag) — test input writer"""
+    e = ">" if big_endian else "<"
+
+    def head(t, top=False):
+        flag = 0x20000000 if (top and srid is not None) else 0
+        b = struct.pack("<B", 0 if big_endian else 1) + struct.pack(e + "I", t | flag)
+        if flag:
+            b += struct.pack(e + "I", srid)
+        return b
+
+    def pts(seq):
+        return b"".join(struct.pack(e + "dd", float(x), float(y)) for x, y in seq)
+
+    def line(seq):
+        return struct.pack(e + "I", len(seq)) + pts(seq)
+
+    def poly(rings):
+        return struct.pack(e + "I", len(rings)) + b"".join(line(r) for r in rings)
+
+    if wkb_type == 1:
+        return head(1, True) + pts([shape])
+    if wkb_type == 2:
+        return head(2, True) + line(shape)
+    if wkb_type == 3:
+        return head(3, True) + poly(shape)
+    if wkb_type == 4:
+        return head(4, True) + struct.pack(e + "I", len(shape)) + b"".join(head(1) + pts([p]) for p in shape)
+    if wkb_type == 5:
+        return head(5, True) + struct.pack(e + "I", len(shape)) + b"".join(head(2) + line(l) for l in shape)
+    if wkb_type == 6:
+        return head(6, True) + struct.pack(e + "I", len(shape)) + b"".join(head(3) + poly(p) for p in shape)
+    raise ValueError(wkb_type)
+
+
+def column(rows):
+    """list of bytes|None -> (int32 offsets, uint8 data, bool valid)"""
+    off = np.zeros(len(rows) + 1, dtype=np.int64)
+    for i, r in enumerate(rows):
+        off[i + 1] = off[i] + (0 if r is None else len(r))
+    data = np.frombuffer(b"".join(r for r in rows if r is not None), dtype=np.uint8).copy()
+    return off, data, np.array([r is not None for r in rows])

@@ -94,6 +94,49 @@ def main():
         row("convex_hull (config 5)", G, "polygons", nc * 16, hv.n_coords * 16, *t)
         res["hull_mean_vertices"] = hv.n_coords / G
         keep.clear()
+        # ---- WKB codec on the same polygons (§8f rank 1): encode to device WKB, decode back ---------------
+        ctx.trim()  # hand the cached affine / hull blocks back: the WKB image of config 5 is another 41 GB
+        wkb_bytes = G * (13 + 16 * (NV + 1))
+        wb = torch.empty(wkb_bytes + 64, dtype=torch.uint8, device=dev)
+        wo = torch.empty(G + 1, dtype=torch.int64, device=dev)
+        t = timed(st, lambda: polys.encode_wkb(64, device_out=(wo.data_ptr(), wb.data_ptr(), wb.numel())), reps=3, warm=1)
+        row("WKB encode, polygons x 257 coords (device to device)", G, "polygons", nc * 16, wkb_bytes, *t)
+
+        def dec():
+            keep["d"] = ctx.decode_wkb(wb.data_ptr(), wo.data_ptr(), None, n=G, offset_width=64, device=True)
+
+        t = timed(st, dec, reps=3, warm=1)
+        dv = keep["d"].view()
+        assert dv.n_coords == nc and dv.n_rings == G
+        out_g = torch.empty(G, dtype=torch.float64, device=dev)  # same areas <=> same rings (bit-exact kernel, same order)
+        E.check(lib.gpl_area(ctx._h, keep["d"]._h, C.c_void_p(out_g.data_ptr()), E.GPL_DEVICE))
+        st.synchronize()
+        assert torch.equal(out_g, out_f), "WKB round trip changed the polygons"
+        del out_g
+        row("WKB decode, polygons x 257 coords (device to device)", G, "polygons", wkb_bytes, nc * 16, *t)
+        keep.clear()
+        del wb, wo
+        # Point columns: 21-byte rows (what data/cities.arrow and the reference's point datasets hold)
+        NP = int(100_000_000 * args.scale)
+        pxy = torch.empty((NP, 2), dtype=torch.float64, device=dev)
+        E.check(lib.gpl_gen_uniform_points(ctx._h, 2, 0, NP, 1000.0, pxy.data_ptr()))
+        pts = ctx.wrap_device(GeometryType.POINT, NP, NP, pxy.data_ptr(), keepalive=(pxy,))
+        wb = torch.empty(NP * 21 + 64, dtype=torch.uint8, device=dev)
+        wo = torch.empty(NP + 1, dtype=torch.int32, device=dev)
+        t = timed(st, lambda: pts.encode_wkb(32, device_out=(wo.data_ptr(), wb.data_ptr(), wb.numel())), reps=3, warm=1)
+        row("WKB encode, points (device to device)", NP, "points", NP * 16, NP * 21 + NP * 4, *t)
+
+        def decp():
+            keep["d"] = ctx.decode_wkb(wb.data_ptr(), wo.data_ptr(), None, n=NP, offset_width=32, device=True)
+
+        t = timed(st, decp, reps=3, warm=1)
+        back = torch.empty((NP, 2), dtype=torch.float64, device=dev)
+        E.check(lib.gpl_array_copy_out(ctx._h, keep["d"]._h, C.c_void_p(back.data_ptr()), None, None, None, None, E.GPL_DEVICE))
+        st.synchronize()
+        assert torch.equal(back, pxy), "WKB round trip changed the points"
+        row("WKB decode, points (device to device)", NP, "points", NP * 21 + NP * 4, NP * 16, *t)
+        keep.clear()
+        del back, wb, wo, pts, pxy
         del polys, xy, ro, go, out_f
         torch.cuda.empty_cache()
         # ---- config 3: N linestring pairs, K = 16 -----------------------------------------------------------
