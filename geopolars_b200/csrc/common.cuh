@@ -143,6 +143,19 @@ void array_retain(gpl_array *a);
 #ifdef __CUDACC__
 namespace gpl {
 
+__device__ __forceinline__ double pt_dist(double2 a, double2 b) { return hypot(b.x - a.x, b.y - a.y); }
+// geo-types private_utils::line_segment_distance (recalled): distance from p to the SEGMENT s-e
+__device__ __forceinline__ double line_segment_distance(double2 p, double2 s, double2 e) {
+    if (s.x == e.x && s.y == e.y) return pt_dist(p, s);
+    double dx = e.x - s.x, dy = e.y - s.y;
+    double d2 = dx * dx + dy * dy;
+    double r = ((p.x - s.x) * dx + (p.y - s.y) * dy) / d2;
+    if (r <= 0.0) return pt_dist(p, s);
+    if (r >= 1.0) return pt_dist(p, e);
+    double sv = ((s.y - p.y) * dx - (s.x - p.x) * dy) / d2;
+    return fabs(sv) * hypot(dx, dy);
+}
+
 __device__ __forceinline__ double2 ld2(const double *xy, int64_t i) {
     return reinterpret_cast<const double2 *>(xy)[i];
 }

@@ -368,18 +368,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_ls_ls_exact(int64_t n, cons
 }
 
 // ---- point vs linestring / polygon -------------------------------------------------------------
-__device__ __forceinline__ double pt_dist(double2 a, double2 b) { return hypot(b.x - a.x, b.y - a.y); }
-// geo-types line_segment_distance (exact restatement, used where a row has few items)
-__device__ __forceinline__ double line_segment_distance(double2 p, double2 s, double2 e) {
-    if (s.x == e.x && s.y == e.y) return pt_dist(p, s);
-    double dx = e.x - s.x, dy = e.y - s.y;
-    double d2 = dx * dx + dy * dy;
-    double r = ((p.x - s.x) * dx + (p.y - s.y) * dy) / d2;
-    if (r <= 0.0) return pt_dist(p, s);
-    if (r >= 1.0) return pt_dist(p, e);
-    double sv = ((s.y - p.y) * dx - (s.x - p.x) * dy) / d2;
-    return fabs(sv) * hypot(dx, dy);
-}
+// pt_dist / line_segment_distance: common.cuh
 // geo-types line_string_contains_point (epsilon based, inexact by design), warp cooperative
 __device__ __forceinline__ bool line_string_contains_point(const double2 *__restrict__ xy, int64_t c0, int64_t n, double2 p,
                                                            int lane) {

@@ -355,6 +355,11 @@ def convex_hull(a: DeviceArray) -> DeviceArray:
     return _out_array(a.ctx, a.ctx.lib.gpl_convex_hull, a._h)
 
 
+def simplify(a: DeviceArray, tolerance: float) -> DeviceArray:
+    """GeoSeries::simplify (geoseries.rs:108-116): geo's Ramer-Douglas-Peucker"""
+    return _out_array(a.ctx, a.ctx.lib.gpl_simplify, a._h, C.c_double(float(tolerance)))
+
+
 def exterior(a: DeviceArray) -> DeviceArray:
     return _out_array(a.ctx, a.ctx.lib.gpl_exterior, a._h)
 

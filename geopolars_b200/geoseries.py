@@ -198,8 +198,9 @@ class GeoRustSeries:
     def skew(self, xs: float = 0.0, ys: float = 0.0, origin: TransformOrigin = "center") -> GeoSeries:
         return self._wrap(E.skew(self._d(), xs, ys, origin))
 
-    def simplify(self, tolerance: float):
-        raise NotImplementedError("simplify (Douglas-Peucker) is outside the hot path built so far (SURVEY.md §8f rank 2)")
+    def simplify(self, tolerance: float) -> GeoSeries:
+        """Douglas-Peucker simplification (geoseries.rs:108-116); end points are always preserved"""
+        return self._wrap(E.simplify(self._d(), tolerance))
 
     def distance(self, other: GeoSeries):
         out, valid = E.distance(self._d(), other.device)

@@ -195,6 +195,10 @@ int gpl_euclidean_length(gpl_ctx *ctx, const gpl_array *in, double *out, int mem
 /* GeoSeries::convex_hull (geoseries.rs:23-26): POLYGON array, one closed CCW ring per geometry, in
  * geo's quick_hull vertex order */
 int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
+/* GeoSeries::simplify (geoseries.rs:108-116, impl :240-242): Ramer-Douglas-Peucker with geo 0.27's minimum-size
+ * guard (2 points per linestring, 4 per polygon ring); LineString / MultiLineString / Polygon / MultiPolygon;
+ * tolerance <= 0 returns the input coordinates.  Outer offsets and validity are shared with the input. */
+int gpl_simplify(gpl_ctx *ctx, const gpl_array *in, double tolerance, gpl_array **out);
 /* GeoSeries::distance (geoseries.rs:141-146), row-wise 1:1; out[n] f64, out_validity bitmap
  * (may be NULL).  Pairs: any of Point / LineString / Polygon on either side (geo EuclideanDistance);
  * other types -> GPL_ERR_INVALID_TYPE.  A row without a single segment where geo needs one is null. */

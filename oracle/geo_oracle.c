@@ -1324,6 +1324,73 @@ int64_t og_convex_hull(const og_array *a, int64_t *out_off, double *out_xy, int 
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* simplify — GeoSeries::simplify geoseries.rs:108-116 ; geo 0.27 simplify.rs (recalled):        */
+/* recursive Ramer-Douglas-Peucker with the INITIAL_MIN guard carried through the recursion     */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct rdp_state {
+    const double *xy; /* the chain's coordinates */
+    uint8_t *keep;
+    double eps;
+    int64_t simplified_len;
+    int64_t min_len;
+} rdp_state;
+/* marks what compute_rdp(&rdp_indices[lo..=hi]) returns */
+static void compute_rdp(rdp_state *s, int64_t lo, int64_t hi) {
+    int64_t len = hi - lo + 1;
+    s->keep[lo] = 1;
+    s->keep[hi] = 1;
+    if (len == 2) return;
+    const double *first = s->xy + 2 * lo, *last = s->xy + 2 * hi;
+    int64_t farthest_index = 0;
+    double farthest_distance = 0.0;
+    for (int64_t i = lo + 1; i < hi; ++i) { /* skip(1).take(len - 1): interior points only */
+        double d = line_segment_distance(s->xy + 2 * i, first, last);
+        if (d >= farthest_distance) {
+            farthest_index = i;
+            farthest_distance = d;
+        }
+    }
+    if (farthest_distance > s->eps) {
+        compute_rdp(s, lo, farthest_index);
+        compute_rdp(s, farthest_index, hi);
+        return;
+    }
+    int64_t number_culled = len - 2;
+    int64_t new_length = s->simplified_len - number_culled;
+    if (new_length < s->min_len) { /* would drop below the minimum: return the slice untouched */
+        for (int64_t i = lo; i <= hi; ++i) s->keep[i] = 1;
+        return;
+    }
+    s->simplified_len = new_length;
+}
+static void rdp_chain(const double *xy, int64_t n, double eps, int64_t min_len, uint8_t *keep) {
+    if (n <= 0) return;
+    if (!(eps > 0.0) || n <= 2) { /* epsilon <= 0 returns the input; n == 1 panics (debug) / misbehaves in geo: kept as is */
+        memset(keep, 1, (size_t)n);
+        return;
+    }
+    memset(keep, 0, (size_t)n);
+    rdp_state s = {xy, keep, eps, n, min_len};
+    compute_rdp(&s, 0, n - 1);
+}
+int og_simplify_mask(const og_array *a, double eps, uint8_t *keep, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    const int64_t *off;
+    int64_t chains, min_len;
+    switch (a->type) {
+    case OG_LINESTRING: off = a->geom_off, chains = a->n, min_len = 2; break;
+    case OG_MULTILINESTRING: off = a->ring_off, chains = a->geom_off[a->n], min_len = 2; break;
+    case OG_POLYGON: off = a->ring_off, chains = a->geom_off[a->n], min_len = 4; break;
+    case OG_MULTIPOLYGON: off = a->ring_off, chains = a->part_off[a->geom_off[a->n]], min_len = 4; break;
+    default: return -1;
+    }
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 256)
+    for (int64_t k = 0; k < chains; ++k) rdp_chain(a->xy + 2 * off[k], off[k + 1] - off[k], eps, min_len, keep + off[k]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* synthetic data — SURVEY.md §8d RNG                                                          */
 /* ------------------------------------------------------------------------------------------- */
 double og_splitmix_u(uint64_t seed, uint64_t counter) {

@@ -52,6 +52,10 @@ typedef struct og_array {
     const uint8_t *valid;    /* Arrow LSB bitmap or NULL */
 } og_array;
 
+/* GeoSeries::simplify (geoseries.rs:108-116): keep[c] = 1 for the coordinates geo's RDP retains (LineString /
+ * MultiLineString minimum 2 points, polygon rings minimum 4); returns -1 for other types */
+int og_simplify_mask(const og_array *arr, double eps, uint8_t *keep, int threads);
+
 /* robust 1.1.0 orient2d (Shewchuk adaptive).  Only the sign is consumed anywhere on the path. */
 double og_orient2d(double ax, double ay, double bx, double by, double cx, double cy);
 /* statistics: how many calls fell through to the adaptive stage since process start */

@@ -213,6 +213,16 @@ def distance_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
     return out
 
 
+def simplify_mask(arr: OGArray, eps: float, threads: int = 1) -> np.ndarray:
+    """bool per input coordinate: retained by geo's Ramer-Douglas-Peucker"""
+    s, k = arr._c()
+    keep = np.zeros(len(arr.xy), dtype=np.uint8)
+    rc = lib().og_simplify_mask(C.byref(s), C.c_double(eps), _p(keep), C.c_int(threads))
+    if rc != 0:
+        raise TypeError("simplify: LineString / MultiLineString / Polygon / MultiPolygon only")
+    return keep.astype(bool)
+
+
 def convex_hull(arr: OGArray, threads: int = 1):
     """returns (ring_off int64[n+1], xy (total,2)) — one closed ring per geometry."""
     s, keep = arr._c()

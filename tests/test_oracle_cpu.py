@@ -216,3 +216,25 @@ def test_polygon_linestring_distance_known_answers(og, conv):
     L = GeoArrowArray.from_shapes(GeometryType.LINESTRING, [[(13, 5), (20, 5)], [(13, 14), (20, 20)], [(4, 5), (6, 5)], [(5, 5), (12, 5)], [(1, 1), (2, 1)]])
     assert og.distance_rowwise(conv(A), conv(L)).tolist() == [3.0, 5.0, 2.0, 0.0, 0.0]
     assert og.distance_rowwise(conv(L), conv(A)).tolist() == [3.0, 5.0, 2.0, 0.0, 0.0]
+
+
+def test_simplify_known_answers(og, conv):
+    """geo's own documentation / unit-test examples for Simplify (recalled), plus the minimum-size guard"""
+    from geopolars_b200 import GeoArrowArray, GeometryType
+
+    ls = [(0.0, 0.0), (5.0, 4.0), (11.0, 5.5), (17.3, 3.2), (27.8, 0.1)]
+    arr = GeoArrowArray.from_shapes(GeometryType.LINESTRING, [ls, ls[:2], [], [(1, 1)], [(0, 0), (1, 0.1), (2, 0)]])
+    keep = og.simplify_mask(conv(arr), 1.0)
+    assert keep[:5].tolist() == [True, True, True, False, True]  # -> (0,0),(5,4),(11,5.5),(27.8,0.1)
+    assert keep[5:8].tolist() == [True, True, True] and keep[8:].tolist() == [True, False, True]
+    assert og.simplify_mask(conv(arr), 0.0).all() and og.simplify_mask(conv(arr), -1.0).all()
+    poly = [(0.0, 0.0), (0.0, 10.0), (5.0, 11.0), (10.0, 10.0), (10.0, 0.0), (0.0, 0.0)]
+    tri = [(0.0, 0.0), (4.0, 0.1), (8.0, 0.0), (4.0, 5.0), (0.0, 0.0)]  # 5 coords: culling (4,0.1) leaves 4 -> allowed
+    sliver = [(0.0, 0.0), (4.0, 0.1), (8.0, 0.0), (0.0, 0.0)]  # 4 coords: any cull would leave < 4 -> untouched
+    parr = GeoArrowArray.from_shapes(GeometryType.POLYGON, [[poly], [tri], [sliver]])
+    keep = og.simplify_mask(conv(parr), 2.0)
+    assert keep[:6].tolist() == [True, True, False, True, True, True]  # -> (0,0),(0,10),(10,10),(10,0),(0,0)
+    assert keep[6:11].tolist() == [True, False, True, True, True]
+    assert keep[11:].all()
+    with pytest.raises(TypeError):
+        og.simplify_mask(conv(GeoArrowArray.points(np.zeros((2, 2)))), 1.0)
