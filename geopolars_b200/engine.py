@@ -355,6 +355,21 @@ def convex_hull(a: DeviceArray) -> DeviceArray:
     return _out_array(a.ctx, a.ctx.lib.gpl_convex_hull, a._h)
 
 
+GEODESIC_METHODS = {"geodesic": 0, "haversine": 1, "vincenty": 2}
+
+
+def geodesic_length(a: DeviceArray, method: str = "geodesic") -> Tuple[np.ndarray, np.ndarray]:
+    """GeoSeries::geodesic_length (geoseries.rs:52-58): metres; (values, valid) — a row is invalid when Vincenty fails"""
+    m = GEODESIC_METHODS.get(str(method).lower())
+    if m is None:
+        raise ValueError("Geodesic calculation method not valid. Use one of geodesic, haversine or vincenty")
+    n = len(a)
+    out = np.empty(n, dtype=np.float64)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    check(a.ctx.lib.gpl_geodesic_length(a.ctx._h, a._h, m, _np_ptr(out), _np_ptr(bm), GPL_HOST))
+    return out, _bits(bm, n)
+
+
 def simplify(a: DeviceArray, tolerance: float) -> DeviceArray:
     """GeoSeries::simplify (geoseries.rs:108-116): geo's Ramer-Douglas-Peucker"""
     return _out_array(a.ctx, a.ctx.lib.gpl_simplify, a._h, C.c_double(float(tolerance)))

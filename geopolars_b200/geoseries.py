@@ -171,7 +171,8 @@ class GeoRustSeries:
     def geodesic_length(self, method: str = "geodesic"):
         if method.lower() not in ("geodesic", "haversine", "vincenty"):
             raise ValueError("Geodesic calculation method not valid. Use one of geodesic, haversine or vincenty")
-        raise NotImplementedError("geodesic_length is outside the GeoSeries hot path built so far (SURVEY.md §8f rank 2)")
+        out, valid = E.geodesic_length(self._d(), method)
+        return _f64(out, valid)
 
     @property
     def geom_type(self):

@@ -192,6 +192,10 @@ int gpl_centroid(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
 int gpl_envelope(gpl_ctx *ctx, const gpl_array *in, gpl_array **out, double *out4, int mem);
 /* GeoSeries::euclidean_length (geoseries.rs:35-41) */
 int gpl_euclidean_length(gpl_ctx *ctx, const gpl_array *in, double *out, int mem);
+/* GeoSeries::geodesic_length (geoseries.rs:52-58; method names py-geopolars/src/geo.rs:64-67): metres, input in
+ * (lon, lat) degrees.  method 0 = geodesic (Karney 2013, WGS84), 1 = haversine, 2 = vincenty.  out_validity
+ * (optional bitmap): a row is null when a Vincenty segment does not converge (the reference returns Err) */
+int gpl_geodesic_length(gpl_ctx *ctx, const gpl_array *in, int method, double *out, uint8_t *out_validity, int mem);
 /* GeoSeries::convex_hull (geoseries.rs:23-26): POLYGON array, one closed CCW ring per geometry, in
  * geo's quick_hull vertex order */
 int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);

@@ -52,6 +52,11 @@ typedef struct og_array {
     const uint8_t *valid;    /* Arrow LSB bitmap or NULL */
 } og_array;
 
+/* GeoSeries::geodesic_length (geoseries.rs:52-58): method 0 geodesic (Karney), 1 haversine, 2 vincenty; metres;
+ * coordinates are (lon, lat) degrees.  NaN where Vincenty does not converge. */
+int og_geodesic_length(const og_array *arr, int method, double *out, int threads);
+double og_geodesic_distance(int method, double lon1, double lat1, double lon2, double lat2);
+
 /* GeoSeries::simplify (geoseries.rs:108-116): keep[c] = 1 for the coordinates geo's RDP retains (LineString /
  * MultiLineString minimum 2 points, polygon rings minimum 4); returns -1 for other types */
 int og_simplify_mask(const og_array *arr, double eps, uint8_t *keep, int threads);

@@ -213,6 +213,24 @@ def distance_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
     return out
 
 
+GEODESIC_METHODS = {"geodesic": 0, "haversine": 1, "vincenty": 2}
+
+
+def geodesic_length(arr: OGArray, method: str = "geodesic", threads: int = 1) -> np.ndarray:
+    s, k = arr._c()
+    out = np.empty(len(arr), dtype=np.float64)
+    rc = lib().og_geodesic_length(C.byref(s), C.c_int(GEODESIC_METHODS[method]), _p(out), C.c_int(threads))
+    assert rc == 0
+    return out
+
+
+def geodesic_distance(method: str, lon1, lat1, lon2, lat2) -> float:
+    L = lib()
+    L.og_geodesic_distance.restype = C.c_double
+    L.og_geodesic_distance.argtypes = [C.c_int] + [C.c_double] * 4
+    return L.og_geodesic_distance(GEODESIC_METHODS[method], lon1, lat1, lon2, lat2)
+
+
 def simplify_mask(arr: OGArray, eps: float, threads: int = 1) -> np.ndarray:
     """bool per input coordinate: retained by geo's Ramer-Douglas-Peucker"""
     s, k = arr._c()

@@ -238,3 +238,29 @@ def test_simplify_known_answers(og, conv):
     assert keep[11:].all()
     with pytest.raises(TypeError):
         og.simplify_mask(conv(GeoArrowArray.points(np.zeros((2, 2)))), 1.0)
+
+
+def test_geodesic_known_answers(og):
+    """pins the oracle's Karney / Vincenty / haversine restatement on published values: the WGS84 quarter
+    meridian, a quarter of the equator, Karney (2013) section 7's near-antipodal example and the inverse of
+    his direct example; Vincenty agrees with Karney where it converges"""
+    g = lambda *a: og.geodesic_distance("geodesic", *a)
+    assert abs(g(0, 0, 0, 90) - 10001965.729) < 1e-3
+    assert abs(g(0, 0, 90, 0) - 6378137.0 * np.pi / 2) < 1e-8
+    assert abs(g(0, 0, 180, 0) - 2 * g(0, 0, 0, 90)) < 1e-8
+    assert abs(g(0, -30, 179.8, 29.9) - 19989832.82761) < 1e-5
+    assert abs(g(0, 40, 137.84490004377, 41.79331020506) - 1e7) < 1e-5
+    assert g(10, 20, 10, 20) == 0.0
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(3000):
+        lo1, lo2 = rng.uniform(-180, 180, 2)
+        la1, la2 = rng.uniform(-89, 89, 2)
+        k, v = g(lo1, la1, lo2, la2), og.geodesic_distance("vincenty", lo1, la1, lo2, la2)
+        if not np.isnan(v):
+            worst = max(worst, abs(k - v) / k)
+        assert abs(k - g(lo2, la2, lo1, la1)) <= 1e-9 * k
+    assert worst < 1e-9
+    assert np.isnan(og.geodesic_distance("vincenty", 0, 0, 180, 0))  # antipodal: FailedToConvergeError
+    # haversine on the mean sphere: a quarter great circle
+    assert abs(og.geodesic_distance("haversine", 0, 0, 90, 0) - 6371008.8 * np.pi / 2) < 1e-6
