@@ -87,7 +87,7 @@ constexpr double K_TOL0 = 2.220446049250313e-16;
 #define K_MAXIT2 (K_MAXIT1 + 53 + 10)
 __device__ __forceinline__ double ksq(double x) { return x * x; }
 __device__ __forceinline__ void knorm2(double *x, double *y) {
-    double r = hypot(*x, *y);
+    double r = gpl_hypot(*x, *y);
     *x /= r;
     *y /= r;
 }
@@ -267,7 +267,7 @@ __device__ __noinline__ double kinverse_start(const kg_t *g, double sbet1, doubl
     }
     salp1 = cbet2 * somg12;
     calp1 = comg12 >= 0 ? sbet12 + cbet2 * sbet1 * ksq(somg12) / (1 + comg12) : sbet12a - cbet2 * sbet1 * ksq(somg12) / (1 - comg12);
-    ssig12 = hypot(salp1, calp1);
+    ssig12 = gpl_hypot(salp1, calp1);
     csig12 = sbet1 * sbet2 + cbet1 * cbet2 * comg12;
     if (shortline && ssig12 < g->etol2) {
         salp2 = cbet1 * somg12;
@@ -320,7 +320,7 @@ __device__ __noinline__ double klambda12(const kg_t *g, double sbet1, double cbe
     double salp0, calp0, somg1, comg1, somg2, comg2, somg12, comg12, lam12, B312, eta, k2, Ca[7];
     if (sbet1 == 0 && calp1 == 0) calp1 = -K_TINY;
     salp0 = salp1 * cbet1;
-    calp0 = hypot(calp1, salp1 * sbet1);
+    calp0 = gpl_hypot(calp1, salp1 * sbet1);
     ssig1 = sbet1;
     somg1 = salp0 * sbet1;
     csig1 = comg1 = calp1 * cbet1;

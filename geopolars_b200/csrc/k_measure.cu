@@ -121,7 +121,7 @@ static __device__ __noinline__ WC line_string_wc(const double2 *__restrict__ xy,
             px += p.x;
             py += p.y;
         } else {
-            double len = hypot(q.x - p.x, q.y - p.y);
+            double len = gpl_hypot(q.x - p.x, q.y - p.y);
             L += len;
             lx += ((q.x + p.x) / 2.0) * len;
             ly += ((q.y + p.y) / 2.0) * len;
@@ -318,7 +318,7 @@ __device__ __forceinline__ double range_length(const double2 *__restrict__ xy, i
     double s = 0.0;
     for (int64_t i = c0 + lane; i < c1 - 1; i += 32) {
         double2 p = xy[i], q = xy[i + 1];
-        s += hypot(q.x - p.x, q.y - p.y);
+        s += gpl_hypot(q.x - p.x, q.y - p.y);
     }
     return s;
 }
