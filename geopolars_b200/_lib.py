@@ -14,7 +14,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgeopolars_b200.so")
+# GEOPOLARS_B200_LIB: load another build of the same library (kernel-variant experiments)
+SO_PATH = os.environ.get("GEOPOLARS_B200_LIB") or os.path.join(_HERE, "libgeopolars_b200.so")
 
 GPL_HOST, GPL_DEVICE = 0, 1
 ORIGIN_CENTROID, ORIGIN_CENTER, ORIGIN_POINT = 0, 1, 2

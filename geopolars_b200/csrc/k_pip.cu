@@ -82,7 +82,12 @@ static_assert(sizeof(CellRec) == 32, "CellRec must be one sector");
 
 constexpr int32_t kFastBit = 1 << 30;  // PartLite::nb_flags: the CellRec points at the FP32 fast table
 constexpr int kFastCShift = 24;        // bits 24..29: C/2 (C = 16-byte records per bucket incl. header, even)
-constexpr int kFastMaxC = 64;
+#ifndef GPL_FAST_LIST
+#define GPL_FAST_LIST 6
+#endif
+constexpr int kFastListRecs = GPL_FAST_LIST;  // records per fast list: header + edges, even (see the FP32 fast table below)
+static_assert(GPL_FAST_LIST % 2 == 0 && GPL_FAST_LIST >= 2 && GPL_FAST_LIST <= 8, "fast list = 1..4 sectors");
+constexpr int kFastMaxCount = 120;  // longest bucket list a fast part may have
 
 struct __align__(32) EdgeRec {  // one L2 sector
     double sx, sy, ex, ey;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts,
                                                       const int64_t *__restrict__ ring_off,
                                                       const uint8_t *__restrict__ validity,
                                                       const int32_t *__restrict__ parent, PartHeader *__restrict__ parts,
-                                                      int32_t *__restrict__ nb_out, int64_t *__restrict__ any_holes) {
+                                                      int32_t *__restrict__ nb_out, int64_t *__restrict__ any_holes, int slots_x100) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -175,9 +180,9 @@ __global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts,
         if (lane == 0) {
             PartHeader h;
             h.xmin = x0, h.ymin = y0, h.xmax = x1, h.ymax = y1;
-            // ~2 edge slots per bucket: measured on the config-2 stars this gives ~6.7 listed edges
-            // per point against 64 for a brute-force ring walk, at 3.3 records per edge of memory.
-            int64_t nb = valid ? (n_slots + 1) / 2 : 0;
+            // ~3 edge slots per y-bucket (slots_x100): on the config-2 stars a bucket lists ~9 of the 64 edges, and
+            // each of its two one-sided lists (FP32 table) ~4.5.
+            int64_t nb = valid ? (n_slots * 100 + slots_x100 - 1) / slots_x100 : 0;
             if (nb < 1) nb = valid ? 1 : 0;
             if (nb > 4096) nb = 4096;
             float yminf = __double2float_rd(y0);
@@ -261,6 +266,11 @@ __global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, c
             }
         }
 }
+// the x that separates the two one-sided edge lists of a part: the middle of its FLOAT x-range, formed the same
+// way by the build kernels (here) and by the query kernel (from PartLite)
+__device__ __forceinline__ double fast_split_x(const PartHeader &h) {
+    return 0.5 * ((double)__double2float_rd(h.xmin) + (double)__double2float_ru(h.xmax));
+}
 __device__ __forceinline__ PartLite lite_of(const PartHeader &h) {
     PartLite l;
     l.xminf = __double2float_rd(h.xmin);
@@ -293,7 +303,7 @@ __global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__rest
     if (b > a) {
         r.lite = lite_of(parts[items[a]]);
         if (b - a == 1 && fast_c[items[a]] > 0) {  // the one-load fast path: parameters of the FP32 table
-            r.lite.nb_flags |= kFastBit | ((fast_c[items[a]] / 2) << kFastCShift);
+            r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
             r.lite.bucket_base = fast_base[items[a]];
         }
     } else {
@@ -313,33 +323,52 @@ __global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_part
     recs[p] = r;
 }
 // ---- FP32 fast table --------------------------------------------------------------------------------
-// The query kernel is bound by the number of 32-byte L2 sectors it pulls per point (measured: 7.5
-// sectors/point at ~90 % of the L2->SM bandwidth), so plain parts (no holes, POLYGON rows, short bucket
-// lists) get a second, denser table:
+// The query kernel lives on L2: per point it pulls one cell sector plus its edge records, and it slows down as
+// soon as the records it touches stop fitting in L2 next to the 1.6 GB point stream.  Plain parts (no holes,
+// POLYGON rows) therefore get a second, denser table:
 //   * edges as four FLOATS relative to the part origin O = (xminf, yminf): 16 bytes, two per sector;
-//   * fixed stride: bucket b of a part starts at fast_base + b*C records, record 0 is a header {count},
-//     unused slots hold an inert sentinel (+inf ordinates) — no (start,end) lookup at all.
-// The floats only feed a FILTER with a rigorous error bound (fast_edge_rule); anything it cannot
-// certify is re-evaluated from the f64 records by the exact kernel.  kFastBit/kFastCShift live in
-// PartLite::nb_flags of the CellRec of a single-candidate cell.
+//   * TWO lists per y-bucket ("sides").  A horizontal line through a spiky ring crosses many edges (12-17 on
+//     the config-2 stars, whatever the bucket height), but only the crossings on ONE side of the point matter
+//     to the winding number.  With xm = the middle of the part's float x-range (fast_split_x), a point with
+//     p.x >= xm reads the list of edges with max(sx,ex) >= xm (the others lie strictly left of it: they neither
+//     cross the rightward ray nor contain p); a point with p.x < xm reads the list of edges with
+//     min(sx,ex) <= xm stored MIRRORED in x (x' = xmaxf - x): mirroring turns "left of p" into "right of p'"
+//     and negates the winding number, and only wn != 0 is consumed;
+//   * fixed stride: list (b, side) of a part starts at fast_base + (2b + side) * kFastListRecs records: one
+//     header {count, overflow offset} + kFastListRecs-1 edge slots, unused slots hold an inert sentinel (+inf
+//     ordinates) — no (start,end) lookup, the whole list is one batch of 256-bit loads.  Longer lists
+//     continue in a per-part overflow area addressed from the header (exactly sized: k_buckets counts both
+//     sides).
+// Measured on config 2 (B200, kernel ms per 100 M points): one list per bucket with stride max+1: 2.57;
+// two lists of 8 records: 2.41 (table 100 MB, L2 hit rate 62 %); of 6 records with exact overflow: 2.03; and
+// with 3 instead of 2 edge slots per bucket (table ~50 MB): 1.95.  4-record lists: 2.02.
+// The floats only feed a FILTER with a rigorous error bound (fast_edge_rule); anything it cannot certify is
+// re-evaluated from the f64 records by the exact kernel.  kFastBit lives in PartLite::nb_flags of the CellRec
+// of a single-candidate cell.
 
-// per part: C (0 = not eligible) and number of 16-byte records
+// per part: eligibility and its number of 16-byte records (main lists + overflow)
 __global__ void k_fast_plan(int type, const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ bcount,
-                            int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots) {
+                            const int2 *__restrict__ side_count, int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartHeader h = parts[p];
-    int32_t c = 0;
+    int32_t c = 0, slots = 0;
     if (type == GPL_POLYGON && (h.flags & 2) && !(h.flags & 1)) {
-        int32_t mx = 0;
-        for (int32_t b = 0; b < h.n_buckets; ++b) mx = max(mx, bcount[h.bucket_base + b]);
-        c = (mx + 1 + 1) & ~1;  // header + edges, rounded up to an even number of 16-byte records
-        if (c > kFastMaxC) c = 0;
+        int32_t mx = 0, ovf = 0;
+        for (int32_t b = 0; b < h.n_buckets; ++b) {
+            mx = max(mx, bcount[h.bucket_base + b]);
+            const int2 sc = side_count[h.bucket_base + b];
+            ovf += ((max(sc.x - (kFastListRecs - 1), 0) + 1) & ~1) + ((max(sc.y - (kFastListRecs - 1), 0) + 1) & ~1);
+        }
+        if (mx <= kFastMaxCount) {
+            c = kFastListRecs;
+            slots = h.n_buckets * 2 * kFastListRecs + ovf;
+        }
     }
     fast_c[p] = c;
-    fast_slots[p] = c * h.n_buckets;
+    fast_slots[p] = slots;
 }
-// one warp per part: write header / float edges / sentinels of every bucket
+// one warp per part: both lists of every bucket (header, float edges, sentinels) and the overflow area
 __global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict__ parts, int64_t n_parts,
                                                    const int32_t *__restrict__ fast_c, const int32_t *__restrict__ fast_base,
                                                    const int32_t *__restrict__ bstart, const EdgeRec *__restrict__ entries,
@@ -348,25 +377,47 @@ __global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict_
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inf = __int_as_float(0x7f800000);
+    const float4 sentinel = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
     for (int64_t p = warp; p < n_parts; p += nwarps) {
-        const int32_t c = fast_c[p];
-        if (c == 0) continue;
+        if (fast_c[p] == 0) continue;
         const PartHeader h = parts[p];
-        const double ox = (double)__double2float_rd(h.xmin), oy = h.by0;
-        for (int32_t t = lane; t < c * h.n_buckets; t += 32) {
-            const int32_t b = t / c, k = t - b * c;
+        const double ox = (double)__double2float_rd(h.xmin), mx = (double)__double2float_ru(h.xmax), oy = h.by0;
+        const double xm = fast_split_x(h);  // == 0.5 * (ox + mx); the query kernel forms it from PartLite
+        float4 *base = fast + (int64_t)fast_base[p];
+        int32_t ovf = h.n_buckets * 2 * kFastListRecs;  // next free overflow record (relative to base, always even)
+        for (int32_t b = 0; b < h.n_buckets; ++b) {
             const int32_t e0 = bstart[h.bucket_base + b], n = bstart[h.bucket_base + b + 1] - e0;
-            float4 r;
-            if (k == 0) {
-                r = make_float4(__int_as_float(n), 0.0f, 0.0f, 0.0f);
-            } else if (k <= n) {
-                const EdgeRec ed = entries[e0 + k - 1];
-                r = make_float4(__double2float_rn(ed.sx - ox), __double2float_rn(ed.sy - oy), __double2float_rn(ed.ex - ox),
-                                __double2float_rn(ed.ey - oy));
-            } else {
-                r = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
+            for (int side = 0; side < 2; ++side) {
+                float4 *list = base + ((int64_t)b * 2 + side) * kFastListRecs;
+                int32_t cnt = 0;
+                for (int32_t c0 = 0; c0 < n; c0 += 32) {
+                    const int32_t j = c0 + lane;
+                    bool sel = false;
+                    EdgeRec ed{0.0, 0.0, 0.0, 0.0};
+                    if (j < n) {
+                        ed = entries[e0 + j];
+                        sel = side == 0 ? fmax(ed.sx, ed.ex) >= xm : fmin(ed.sx, ed.ex) <= xm;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, sel);
+                    if (sel) {
+                        const int32_t rank = cnt + __popc(m & ((1u << lane) - 1u));
+                        const float4 r = side == 0 ? make_float4(__double2float_rn(ed.sx - ox), __double2float_rn(ed.sy - oy),
+                                                                 __double2float_rn(ed.ex - ox), __double2float_rn(ed.ey - oy))
+                                                   : make_float4(__double2float_rn(mx - ed.sx), __double2float_rn(ed.sy - oy),
+                                                                 __double2float_rn(mx - ed.ex), __double2float_rn(ed.ey - oy));
+                        if (rank < kFastListRecs - 1) list[1 + rank] = r;
+                        else base[ovf + rank - (kFastListRecs - 1)] = r;
+                    }
+                    cnt += __popc(m);
+                }
+                const int32_t novf = max(cnt - (kFastListRecs - 1), 0), novf2 = (novf + 1) & ~1;
+                if (lane < kFastListRecs - 1 && lane >= cnt) list[1 + lane] = sentinel;
+                if (lane == 0) {
+                    list[0] = make_float4(__int_as_float(cnt), __int_as_float(novf ? ovf : 0), 0.0f, 0.0f);
+                    if (novf2 > novf) base[ovf + novf] = sentinel;
+                }
+                ovf += novf2;
             }
-            fast[(int64_t)fast_base[p] + t] = r;
         }
     }
 }
@@ -402,13 +453,15 @@ __global__ void __launch_bounds__(256) k_buckets(int type, int64_t n_parts, cons
                                                  const int64_t *__restrict__ part_off,
                                                  const int64_t *__restrict__ ring_off,
                                                  const PartHeader *__restrict__ parts,
-                                                 int32_t *__restrict__ count_or_cursor, int64_t *__restrict__ entry_edge) {
+                                                 int32_t *__restrict__ count_or_cursor, int64_t *__restrict__ entry_edge,
+                                                 int2 *__restrict__ side_count) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t p = warp; p < n_parts; p += nwarps) {
         PartHeader h = parts[p];
         if (!(h.flags & 2)) continue;
+        const double xm = fast_split_x(h);
         int64_t r0, r1;
         part_rings(type, p, geom_off, part_off, r0, r1);
         for (int64_t r = r0; r < r1; ++r) {
@@ -427,6 +480,9 @@ __global__ void __launch_bounds__(256) k_buckets(int type, int64_t n_parts, cons
                 for (int32_t b = b0; b <= b1; ++b) {
                     if (PASS == 0) {
                         atomicAdd(&count_or_cursor[h.bucket_base + b], 1);
+                        // lengths of the two one-sided lists of the FP32 table (same predicate as k_fast_fill)
+                        if (fmax(s.x, e.x) >= xm) atomicAdd(&side_count[h.bucket_base + b].x, 1);
+                        if (fmin(s.x, e.x) <= xm) atomicAdd(&side_count[h.bucket_base + b].y, 1);
                     } else {
                         int32_t pos = atomicAdd(&count_or_cursor[h.bucket_base + b], 1);
                         entry_edge[pos] = c;
@@ -694,15 +750,17 @@ __device__ __forceinline__ void ld256f(const float4 *p, float4 &a, float4 &b) {
 }
 // returns Polygon::contains for a plain part when `undecided` stays false
 __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const PartLite &l, double px, double py, bool &undecided) {
-    if (!(px >= (double)l.xminf && px <= (double)l.xmaxf)) return false;
+    const double xlo = (double)l.xminf, xhi = (double)l.xmaxf;
+    if (!(px >= xlo && px <= xhi)) return false;
     const int32_t nb = l.nb_flags & 0x00ffffff;
-    const int32_t C = ((l.nb_flags >> kFastCShift) & 63) * 2;
-    const float qx = __double2float_rn(px - (double)l.xminf), qy = __double2float_rn(py - (double)l.yminf);
+    const bool right = px >= 0.5 * (xlo + xhi);  // which side's list (k_fast_fill uses the same midpoint)
+    const float qx = __double2float_rn(right ? px - xlo : xhi - px), qy = __double2float_rn(py - (double)l.yminf);
     const float tq = qy * l.inv_hf;
     // qy < 0 <=> p.y < yminf <= ymin ; tq >= nb + 1 => p.y > ymax : no listed edge can act
     if (qy < 0.0f || !(tq < (float)(nb + 1))) return false;
     const int32_t b = min((int32_t)tq, nb - 1);
-    const float4 *rec = fast + (int64_t)l.bucket_base + (int64_t)b * C;
+    const float4 *part = fast + (int64_t)l.bucket_base;
+    const float4 *rec = part + (b * 2 + (right ? 0 : 1)) * kFastListRecs;
     const float height = l.inv_hf > 0.0f ? __fdividef((float)nb, l.inv_hf) : 0.0f;  // 2 ulp is plenty: R only feeds bounds with 2x slack
     const float R = fmaxf(l.xmaxf - l.xminf, height);
     const float eta = 9.5367431640625e-07f * R;                          // 2^-20 R
@@ -710,26 +768,24 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     const float inf = __int_as_float(0x7f800000);
     int wn = 0;
     bool und = false;
-    // first batch: header + up to 7 edges (4 sectors), issued together; sentinels make the count irrelevant here
-    float4 r[8];
+    // the list: header + (kFastListRecs - 1) edges, issued together; sentinels make the count irrelevant here
+    float4 r[kFastListRecs];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        r[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
-        r[2 * j + 1] = r[2 * j];
-        if (2 * j < C) ld256f(rec + 2 * j, r[2 * j], r[2 * j + 1]);
-    }
+    for (int j = 0; j < kFastListRecs / 2; ++j) ld256f(rec + 2 * j, r[2 * j], r[2 * j + 1]);
     const int32_t count = __float_as_int(r[0].x);
+    const float4 *more = part + __float_as_int(r[0].y) - kFastListRecs;  // records kFastListRecs.. : the part's overflow area
 #pragma unroll
-    for (int j = 1; j < 8; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
-    for (int32_t k = 8; k <= count; k += 8) {  // records 8.. : only for lists longer than 7
+    for (int j = 1; j < kFastListRecs; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
+    for (int32_t k = kFastListRecs; k <= count; k += 4) {  // longer lists: four more edges per round (2 sectors)
+        float4 t[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            r[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
-            r[2 * j + 1] = r[2 * j];
-            if (k + 2 * j <= count) ld256f(rec + k + 2 * j, r[2 * j], r[2 * j + 1]);  // slots past `count` are sentinels
+        for (int j = 0; j < 2; ++j) {
+            t[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
+            t[2 * j + 1] = t[2 * j];
+            if (k + 2 * j <= count) ld256f(more + k + 2 * j, t[2 * j], t[2 * j + 1]);  // slots past `count` are sentinels
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
+        for (int j = 0; j < 4; ++j) fast_edge_rule(t[j], qx, qy, eta, B, wn, und);
     }
     undecided = undecided || und;
     return wn != 0;
@@ -1085,8 +1141,15 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     }
     const int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Pa, 8), (int64_t)kSMs * 8));
     CUDAF(cudaMemsetAsync(totals.p, 0, sizeof(int64_t) * 8, st));
+    // edge slots per y-bucket x 100.  Measured on config 2 (B200, kernel ms): 133: 2.18, 200: 2.03, 300: 1.95,
+    // 400: 1.98, 500: 2.07 — fewer, longer buckets keep the FP32 table (and the cell grid) inside L2.
+    static const int slots_x100 = [] {
+        const char *e = getenv("GPL_PIP_SLOTS_X100");
+        const int v = e ? atoi(e) : 300;
+        return v >= 25 && v <= 6400 ? v : 300;
+    }();
     k_part_headers<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, polys->validity,
-                                          parent_p, hdr.p, nb.p, totals.p + 4);
+                                          parent_p, hdr.p, nb.p, totals.p + 4, slots_x100);
     ctx->launches++;
     CUDAF(cudaGetLastError());
 
@@ -1107,18 +1170,22 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, cell_count.p, n_cells, cell_start.p, totals.p)));
 
-    // bucket bases and per-bucket entry counts (sum of n_buckets <= P + n_coords/2 + 1: no host round trip)
+    // bucket bases and per-bucket entry counts (sum of n_buckets <= P + n_coords*100/slots_x100 + 1: no host round trip)
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, nb.p, P, base.p, totals.p + 1)));
     if (P > 0) {
         k_set_bucket_base<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, base.p, P);
         ctx->launches++;
     }
-    const int64_t NB_cap = Pa + polys->n_coords / 2 + 1;
+    const int64_t NB_cap = Pa + (polys->n_coords * 100) / slots_x100 + 1;
     TRYF(bcount.get(ctx, (size_t)NB_cap + 1));
     TRYF(bstart.get(ctx, (size_t)NB_cap + 1));
     CUDAF(cudaMemsetAsync(bcount.p, 0, sizeof(int32_t) * (NB_cap + 1), st));
+    Scratch<int2> side_count;  // per bucket: lengths of its two one-sided lists (FP32 table)
+    TRYF(side_count.get(ctx, (size_t)NB_cap + 1));
+    CUDAF(cudaMemsetAsync(side_count.p, 0, sizeof(int2) * (NB_cap + 1), st));
     if (P > 0) {
-        k_buckets<0><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p, nullptr);
+        k_buckets<0><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p, nullptr,
+                                            side_count.p);
         ctx->launches++;
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, bcount.p, NB_cap, bstart.p, totals.p + 2)));
@@ -1127,7 +1194,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(fast_slots.get(ctx, (size_t)Pa + 1));
     TRYF(fast_base.get(ctx, (size_t)Pa + 1));
     if (P > 0) {
-        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, fast_c.p, fast_slots.p);
+        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, side_count.p, fast_c.p, fast_slots.p);
         ctx->launches++;
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, fast_slots.p, P, fast_base.p, totals.p + 3)));
@@ -1201,7 +1268,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         k_part_recs<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, P, idx->parts);
         CUDAF(cudaMemcpyAsync(bcount.p, bstart.p, sizeof(int32_t) * NB_cap, cudaMemcpyDeviceToDevice, st));  // cursors
         k_buckets<1><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p,
-                                            entry_edge.p);
+                                            entry_edge.p, nullptr);
         const int64_t nbk = idx->n_buckets > 0 ? idx->n_buckets : 1;
         k_sort_segments<int64_t><<<(int)ceil_div(nbk, 128), 128, 0, st>>>(entry_edge.p, bstart.p, idx->n_buckets);
         k_materialise<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bstart.p,

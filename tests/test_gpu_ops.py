@@ -222,8 +222,9 @@ def test_point_distances_and_rowwise_contains(ctx, og, conv):
     assert np.array_equal(got, want) and want.any()
     from geopolars_b200 import MismatchedGeometry, ShapeError
 
-    with pytest.raises(MismatchedGeometry):
-        E.distance(dS, dS)
+    assert (E.distance(dS, dS)[0] == 0.0).all()  # Polygon x Polygon is on the path (k_distance_generic)
+    with pytest.raises(MismatchedGeometry):  # Multi* distance is not
+        E.distance(dS, ctx.upload(GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, [[(0.0, 0.0)]] * n)))
     with pytest.raises(ShapeError):
         E.distance(dP, ctx.upload(GeoArrowArray.points(np.zeros((3, 2)))))
 
