@@ -147,8 +147,13 @@ def test_geoseries_accessor_surface(ctx):
     assert len(lhs) >= sum(inside)
     l2, r2 = G.spatial_join(cen, gs, how="left")
     assert set(l2.tolist()) == set(range(177))
-    with pytest.raises(NotImplementedError):
-        geo.simplify(0.1)
+    simp = geo.simplify(0.1)
+    assert len(simp) == 177 and simp.device.view().n_coords < gs.device.view().n_coords
+    assert (np.asarray(simp.geo.area) > 0).all()
+    lengths = {m: np.asarray(geo.geodesic_length(m)) for m in ("geodesic", "haversine", "vincenty")}
+    ok = ~np.isnan(lengths["vincenty"].astype(float))  # country outlines: lon/lat degrees -> metres
+    assert ok.sum() >= 170 and rel_close(lengths["geodesic"][ok], lengths["vincenty"][ok], 1e-5)
+    assert rel_close(lengths["geodesic"], lengths["haversine"], 1e-2) and lengths["geodesic"].min() > 1e4
     with pytest.raises(ValueError):
         geo.geodesic_length("nope")
 
