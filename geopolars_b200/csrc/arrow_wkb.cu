@@ -335,13 +335,18 @@ extern "C" int gpl_array_export_arrow(gpl_ctx *ctx, const gpl_array *a, void *ou
     };
     std::vector<Level> lv;
     const char *ext = "geoarrow.point";
-    switch (h.type) {
+    switch (h.type) {  // (push_back rather than brace assignment: GCC 13 reports a spurious -Wnonnull on the latter)
     case GPL_POINT: break;
-    case GPL_LINESTRING: lv = {{&h.geom, "vertices"}}, ext = "geoarrow.linestring"; break;
-    case GPL_MULTIPOINT: lv = {{&h.geom, "points"}}, ext = "geoarrow.multipoint"; break;
-    case GPL_POLYGON: lv = {{&h.ring, "vertices"}, {&h.geom, "rings"}}, ext = "geoarrow.polygon"; break;
-    case GPL_MULTILINESTRING: lv = {{&h.ring, "vertices"}, {&h.geom, "linestrings"}}, ext = "geoarrow.multilinestring"; break;
-    case GPL_MULTIPOLYGON: lv = {{&h.ring, "vertices"}, {&h.part, "rings"}, {&h.geom, "polygons"}}, ext = "geoarrow.multipolygon"; break;
+    case GPL_LINESTRING: lv.push_back({&h.geom, "vertices"}), ext = "geoarrow.linestring"; break;
+    case GPL_MULTIPOINT: lv.push_back({&h.geom, "points"}), ext = "geoarrow.multipoint"; break;
+    case GPL_POLYGON: lv.push_back({&h.ring, "vertices"}), lv.push_back({&h.geom, "rings"}), ext = "geoarrow.polygon"; break;
+    case GPL_MULTILINESTRING:
+        lv.push_back({&h.ring, "vertices"}), lv.push_back({&h.geom, "linestrings"}), ext = "geoarrow.multilinestring";
+        break;
+    case GPL_MULTIPOLYGON:
+        lv.push_back({&h.ring, "vertices"}), lv.push_back({&h.part, "rings"}), lv.push_back({&h.geom, "polygons"});
+        ext = "geoarrow.multipolygon";
+        break;
     default:
         set_error("cannot export geometry type %d", h.type);
         return GPL_ERR_INVALID_TYPE;

@@ -315,8 +315,7 @@ __device__ __noinline__ double kinverse_start(const kg_t *g, double sbet1, doubl
 __device__ __noinline__ double klambda12(const kg_t *g, double sbet1, double cbet1, double dn1, double sbet2, double cbet2, double dn2, double salp1,
                         double calp1, double slam120, double clam120, double *psig12, double *pssig1, double *pcsig1, double *pssig2,
                         double *pcsig2, double *peps, int diffp, double *pdlam12) {
-    double salp2, calp2, sig12, ssig1, csig1, ssig2, csig2, eps, domg12, dlam12 = 0;
-    (void)salp2;
+    double calp2, sig12, ssig1, csig1, ssig2, csig2, eps, domg12, dlam12 = 0;
     double salp0, calp0, somg1, comg1, somg2, comg2, somg12, comg12, lam12, B312, eta, k2, Ca[7];
     if (sbet1 == 0 && calp1 == 0) calp1 = -K_TINY;
     salp0 = salp1 * cbet1;
@@ -325,7 +324,6 @@ __device__ __noinline__ double klambda12(const kg_t *g, double sbet1, double cbe
     somg1 = salp0 * sbet1;
     csig1 = comg1 = calp1 * cbet1;
     knorm2(&ssig1, &csig1);
-    salp2 = cbet2 != cbet1 ? salp0 / cbet2 : salp1;
     calp2 = cbet2 != cbet1 || fabs(sbet2) != -sbet1
                 ? sqrt(ksq(calp1 * cbet1) + (cbet1 < -sbet1 ? (cbet2 - cbet1) * (cbet1 + cbet2) : (sbet1 - sbet2) * (sbet1 + sbet2))) / cbet2
                 : fabs(calp1);

@@ -96,13 +96,19 @@ __device__ __forceinline__ void count_polygon(Cur &c, RowCounts &k) {
 
 template <typename Off>
 __global__ void __launch_bounds__(256) k_wkb_count(int64_t n, const uint8_t *__restrict__ bytes, const Off *__restrict__ off,
-                                                   const uint8_t *__restrict__ valid, int32_t *__restrict__ cc, int32_t *__restrict__ rr,
-                                                   int32_t *__restrict__ qq, uint8_t *__restrict__ row_valid,
+                                                   const uint8_t *__restrict__ valid, int64_t total_bytes, int32_t *__restrict__ cc,
+                                                   int32_t *__restrict__ rr, int32_t *__restrict__ qq, uint8_t *__restrict__ row_valid,
                                                    unsigned *__restrict__ seen, unsigned long long *__restrict__ bad_row) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t b0 = (int64_t)off[i] - (int64_t)off[0], b1 = (int64_t)off[i + 1] - (int64_t)off[0];
     RowCounts k{0, 0, 0};
+    if (b0 < 0 || b1 < b0 || b1 > total_bytes) {  // offsets must be monotone and inside the payload: never read outside it
+        atomicMin(bad_row, (unsigned long long)i);
+        cc[i] = rr[i] = qq[i] = 0;
+        row_valid[i] = 0;
+        return;
+    }
     bool isnull = !bit_get(valid, i) || b1 - b0 < 5;
     if (!isnull) {
         Cur c{bytes + b0, bytes + b1, true, true};
@@ -420,7 +426,7 @@ static int decode(gpl_ctx *ctx, const uint8_t *bytes_d, const Off *off_d, const 
     h_meta[1] = (int64_t)ULLONG_MAX;
     GPL_CUDA(cudaMemcpyAsync(meta.p, h_meta, sizeof(h_meta), cudaMemcpyHostToDevice, ctx->stream));
     if (n > 0)
-        GPL_LAUNCH(ctx, (k_wkb_count<Off>), (int)ceil_div(n, 256), 256, 0, n, bytes_d, off_d, valid_d, cc.p, rr.p, qq.p, rv.p,
+        GPL_LAUNCH(ctx, (k_wkb_count<Off>), (int)ceil_div(n, 256), 256, 0, n, bytes_d, off_d, valid_d, total_bytes, cc.p, rr.p, qq.p, rv.p,
                    reinterpret_cast<unsigned *>(meta.p), reinterpret_cast<unsigned long long *>(meta.p + 1));
     GPL_TRY((exclusive_scan<int32_t, int64_t>(ctx, cc.p, n, cs.p, meta.p + 2)));
     GPL_TRY((exclusive_scan<int32_t, int64_t>(ctx, rr.p, n, rs.p, meta.p + 3)));
@@ -428,7 +434,8 @@ static int decode(gpl_ctx *ctx, const uint8_t *bytes_d, const Off *off_d, const 
     GPL_CUDA(cudaMemcpyAsync(h_meta, meta.p, sizeof(h_meta), cudaMemcpyDeviceToHost, ctx->stream));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     GPL_REQUIRE((unsigned long long)h_meta[1] == ULLONG_MAX, GPL_ERR_INVALID_ARG,
-                "row %lld: truncated, malformed or unsupported WKB (XY Point..MultiPolygon only)", (long long)h_meta[1]);
+                "row %lld: truncated, malformed or unsupported WKB (XY Point..MultiPolygon only), or offsets out of order",
+                (long long)h_meta[1]);
     const unsigned seen = (unsigned)(h_meta[0] & 0xffffffffu);
     auto has = [&](int code) { return (seen >> code) & 1u; };
     const bool pt = has(GPL_POINT) || has(GPL_MULTIPOINT), ls = has(GPL_LINESTRING) || has(GPL_MULTILINESTRING),

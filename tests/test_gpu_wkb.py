@@ -98,6 +98,11 @@ def test_malformed_input_is_reported_with_its_row(ctx):
     off, data, _ = wkbutil.column(mixed)
     with pytest.raises(MismatchedGeometry):
         ctx.decode_wkb(data, off)
+    off, data, _ = wkbutil.column(raw[:10])
+    bad = off.copy()
+    bad[4], bad[5] = bad[5], bad[4]  # offsets out of order (row 4 ends before it starts): reported, never dereferenced
+    with pytest.raises(GeopolarsError, match="row 4"):
+        ctx.decode_wkb(data, bad)
     empty = ctx.decode_wkb(np.zeros(0, np.uint8), np.zeros(1, np.int32))
     assert len(empty) == 0
 
