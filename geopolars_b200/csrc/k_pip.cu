@@ -120,6 +120,8 @@ struct gpl_pip_index {
     size_t hot_bytes = 0;             // leading part of the slab the L2 persisting window covers (0 = all)
     bool multi = false;               // MULTIPOLYGON: parts[].geom differs from the part id
     bool any_holes = false;
+    bool lean_ok = false;             // every non-empty cell is a single plain FP32-table candidate: k_pip_query<0, LEAN>
+    int64_t n_not_fast = 0;           // valid parts without FP32 lists
     unsigned long long *n_deferred = nullptr;  // device counter inside the slab
     uint32_t *deferred_list = nullptr;         // indices of deferred points (grown on demand)
     uint32_t deferred_cap = 0;
@@ -247,7 +249,7 @@ __device__ __forceinline__ int32_t mono_index(double v, double lo, double inv, i
 // bbox overlaps.
 template <int PASS>
 __global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, const GridParams *__restrict__ gp,
-                        int32_t *__restrict__ count_or_cursor, int32_t *__restrict__ items) {
+                        int32_t *__restrict__ count_or_cursor, int32_t *__restrict__ items, int64_t *__restrict__ any_shared_cell) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartHeader h = parts[p];
@@ -259,7 +261,7 @@ __global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, c
         for (int32_t cx = cx0; cx <= cx1; ++cx) {
             int64_t c = (int64_t)cy * g.gx + cx;
             if (PASS == 0) {
-                atomicAdd(&count_or_cursor[c], 1);
+                if (atomicAdd(&count_or_cursor[c], 1) > 0) *any_shared_cell = 1;  // a cell with several candidates exists
             } else {
                 int32_t pos = atomicAdd(&count_or_cursor[c], 1);
                 items[pos] = (int32_t)p;
@@ -312,14 +314,19 @@ __global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__rest
     }
     cells[c] = r;
 }
-__global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_parts, PartRec *__restrict__ recs) {
+__global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ fast_c,
+                            const int32_t *__restrict__ fast_base, PartRec *__restrict__ recs) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartHeader h = parts[p];
     PartRec r;
-    r.lite = lite_of(h);
+    r.lite = lite_of(h);  // bucket_base: the f64 bucket table (general path, exact kernel)
     r.geom = h.geom;
     r.pad = 0;
+    if (fast_c[p] > 0) {  // the FP32 lists of this part, for candidates read through the PartRec (LEAN kernel)
+        r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
+        r.pad = fast_base[p];
+    }
     recs[p] = r;
 }
 // ---- FP32 fast table --------------------------------------------------------------------------------
@@ -348,7 +355,8 @@ __global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_part
 
 // per part: eligibility and its number of 16-byte records (main lists + overflow)
 __global__ void k_fast_plan(int type, const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ bcount,
-                            const int2 *__restrict__ side_count, int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots) {
+                            const int2 *__restrict__ side_count, int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots,
+                            unsigned long long *__restrict__ n_not_fast) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartHeader h = parts[p];
@@ -365,6 +373,7 @@ __global__ void k_fast_plan(int type, const PartHeader *__restrict__ parts, int6
             slots = h.n_buckets * 2 * kFastListRecs + ovf;
         }
     }
+    if ((h.flags & 2) && c == 0) atomicAdd(n_not_fast, 1ULL);  // a valid part the FP32 table cannot hold
     fast_c[p] = c;
     fast_slots[p] = slots;
 }
@@ -803,8 +812,17 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
 // Further candidates of the cell (overlapping bboxes) and MULTIPOLYGON rows read one 32-byte PartRec each.
 // No function calls and no adaptive-precision code in MODE 0: the register budget stays at 64 with
 // four CTAs per SM.
-template <int MODE>
-__global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const IndexView ix, const double2 *__restrict__ pts,
+#ifndef GPL_PIP_LEAN_MINB
+#define GPL_PIP_LEAN_MINB 4
+#endif
+// LEAN (MODE 0 only): every part of the index is a plain POLYGON with FP32 lists (the host checks it), so the
+// f64 bucket walk is compiled out and further candidates of a cell run the same FP32 walk from their PartRec —
+// 64 instead of 78 registers, four instead of three resident CTAs per SM.  Measured on config 2 (kernel ms per
+// 100 M points): full kernel 1.93, LEAN at 4 CTAs/SM 1.66, LEAN capped at 47 registers for 5 CTAs/SM (spills) 1.86.  A candidate that would still need
+// the f64 walk is deferred to the exact kernel (cannot happen when the host check holds; kept so that the
+// kernel is correct on any index).
+template <int MODE, bool LEAN = false>
+__global__ void __launch_bounds__(kQueryThreads, LEAN ? GPL_PIP_LEAN_MINB : GPL_PIP_MINB) k_pip_query(const IndexView ix, const double2 *__restrict__ pts,
                                                                            const uint8_t *__restrict__ pts_validity,
                                                                            int64_t n_pts, int32_t *__restrict__ first_id,
                                                                            int32_t *__restrict__ count,
@@ -866,9 +884,54 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_MINB) k_pip_query(const
                         }
                         break;
                     }
+                    if (LEAN && n_cand == 1) {  // a lone candidate without FP32 lists
+                        undecided = true;
+                        break;
+                    }
+                    if (LEAN) {  // every candidate through its FP32 lists; anything else goes to the exact kernel
+                        int32_t q[8];
+                        const int32_t cand = __ldg(ix.cell_items + first_part + c);
+                        ld256(ix.parts + cand, q);
+                        PartLite fl;
+                        unpack_lite(q, fl);
+                        fl.bucket_base = q[7];  // PartRec::pad = base of the part's FP32 lists
+                        bool und = !(fl.nb_flags & kFastBit);
+                        const bool inside = !und && fast_walk(ix.fast, fl, p.x, p.y, und);
+                        if (und) {
+                            undecided = true;
+                            break;
+                        }
+                        if (inside) {
+                            if (first < 0) first = cand;
+                            ++cnt;
+                            if (count == nullptr) break;
+                        }
+                        continue;
+                    }
                     if (n_cand > 1) part = __ldg(ix.cell_items + first_part);
                     geom = part;
                 } else {
+                    if (LEAN) {  // every candidate through its FP32 lists; anything else goes to the exact kernel
+                        int32_t q[8];
+                        const int32_t cand = __ldg(ix.cell_items + first_part + c);
+                        ld256(ix.parts + cand, q);
+                        PartLite fl;
+                        unpack_lite(q, fl);
+                        fl.bucket_base = q[7];  // PartRec::pad = base of the part's FP32 lists
+                        bool und = !(fl.nb_flags & kFastBit);
+                        const bool inside = !und && fast_walk(ix.fast, fl, p.x, p.y, und);
+                        if (und) {
+                            undecided = true;
+                            break;
+                        }
+                        if (inside) {
+                            if (first < 0) first = cand;
+                            ++cnt;
+                            if (count == nullptr) break;
+                        }
+                        continue;
+                    }
+
                     if (n_cand > 1) part = __ldg(ix.cell_items + first_part + c);
                     int32_t q[8];
                     ld256(ix.parts + part, q);
@@ -1000,12 +1063,17 @@ static IndexView view_of(const gpl_pip_index *idx) {
     return v;
 }
 
-static int query_grid(int64_t n) {
+static int query_grid(int64_t n, bool lean = false) {
     // persistent-style: 148 SMs x resident CTAs, grid-stride over the point stream
-    static const int per_sm = []() {
+    static const int per_sm_full = []() {
         const char *e = getenv("GPL_PIP_CTAS_PER_SM");
         return e ? atoi(e) : 8;
     }();
+    static const int per_sm_lean = []() {  // two waves of the resident CTAs of the LEAN kernel
+        const char *e = getenv("GPL_PIP_LEAN_CTAS_PER_SM");
+        return e ? atoi(e) : 2 * GPL_PIP_LEAN_MINB;
+    }();
+    const int per_sm = lean ? per_sm_lean : per_sm_full;
     int64_t want = ceil_div(n, kQueryThreads);
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
@@ -1029,10 +1097,16 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
             mut->deferred_cap = cap;
         }
         GPL_CUDA(cudaMemsetAsync(idx->n_deferred, 0, sizeof(unsigned long long), stream));
-        k_pip_query<0><<<query_grid(m), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr, m,
-                                                                      first_dev + lo, count_dev ? count_dev + lo : nullptr, nullptr,
-                                                                      nullptr, nullptr, lo, idx->n_deferred, idx->deferred_list,
-                                                                      idx->deferred_cap);
+        if (idx->lean_ok)
+            k_pip_query<0, true><<<query_grid(m, true), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr,
+                                                                                m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
+                                                                                nullptr, nullptr, nullptr, lo, idx->n_deferred,
+                                                                                idx->deferred_list, idx->deferred_cap);
+        else
+            k_pip_query<0, false><<<query_grid(m), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr,
+                                                                                 m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
+                                                                                 nullptr, nullptr, nullptr, lo, idx->n_deferred,
+                                                                                 idx->deferred_list, idx->deferred_cap);
         k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
                                                      idx->n_deferred, idx->deferred_list, idx->deferred_cap);
         ctx->launches += 2;
@@ -1165,7 +1239,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(cell_start.get(ctx, (size_t)n_cells + 1));
     CUDAF(cudaMemsetAsync(cell_count.p, 0, sizeof(int32_t) * (n_cells + 1), st));
     if (P > 0) {
-        k_cells<0><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, nullptr);
+        k_cells<0><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, nullptr, totals.p + 6);
         ctx->launches++;
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, cell_count.p, n_cells, cell_start.p, totals.p)));
@@ -1194,14 +1268,15 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(fast_slots.get(ctx, (size_t)Pa + 1));
     TRYF(fast_base.get(ctx, (size_t)Pa + 1));
     if (P > 0) {
-        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, side_count.p, fast_c.p, fast_slots.p);
+        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, side_count.p, fast_c.p, fast_slots.p,
+                                                           reinterpret_cast<unsigned long long *>(totals.p + 5));
         ctx->launches++;
     }
     TRYF((exclusive_scan<int32_t, int32_t>(ctx, fast_slots.p, P, fast_base.p, totals.p + 3)));
 
     // the data-dependent sizes + the grid parameters: one small D2H (index build is once per join)
-    int64_t h_tot[5];
-    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, st));
+    int64_t h_tot[7];
+    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 7, cudaMemcpyDeviceToHost, st));
     CUDAF(cudaMemcpyAsync(&idx->grid, gp.p, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
     CUDAF(cudaStreamSynchronize(st));
     idx->n_overflow = h_tot[0];  // all cell items
@@ -1214,6 +1289,8 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         return fail(GPL_ERR_UNSUPPORTED);
     }
     idx->any_holes = h_tot[4] != 0;  // set on the device: ring counts alone cannot tell (an empty polygon next to one with a hole)
+    idx->n_not_fast = h_tot[5];
+    const bool shared_cells = h_tot[6] != 0;
     idx->multi = type == GPL_MULTIPOLYGON;
 
     // ---- phase 2: one slab, filled in place ----------------------------------------------------------
@@ -1232,6 +1309,15 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     const size_t o_items = carve(sizeof(int32_t) * (idx->n_overflow + 1));
     const size_t o_defer = carve(sizeof(unsigned long long));
     const bool all_fast = idx->n_fast > 0 && !idx->multi && !idx->any_holes;
+    {
+        static const bool lean_enabled = [] {
+            const char *e = getenv("GPL_PIP_LEAN");
+            return !e || atoi(e) != 0;  // GPL_PIP_LEAN=0 forces the full kernel (A/B measurements)
+        }();
+        // POLYGON rows without holes, every valid part has FP32 lists (cells may hold several candidates)
+        idx->lean_ok = lean_enabled && all_fast && idx->n_not_fast == 0;
+        (void)shared_cells;
+    }
     const size_t hot_mark = off;
     const size_t o_entries = carve(sizeof(EdgeRec) * (idx->n_entries + 1));
     const size_t o_ring = idx->any_holes ? carve(sizeof(int32_t) * (idx->n_entries + 1)) : 0;
@@ -1254,7 +1340,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(entry_edge.get(ctx, (size_t)idx->n_entries + 1));
     if (P > 0) {
         CUDAF(cudaMemcpyAsync(cell_count.p, cell_start.p, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToDevice, st));  // cursors
-        k_cells<1><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, idx->cell_overflow);
+        k_cells<1><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, idx->cell_overflow, nullptr);
         ctx->launches++;
     }
     k_cell_finish<<<(int)ceil_div(n_cells, 128), 128, 0, st>>>(idx->cells, cell_start.p, idx->cell_overflow, hdr.p, fast_c.p, fast_base.p,
@@ -1265,7 +1351,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         ctx->launches++;
     }
     if (P > 0) {
-        k_part_recs<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, P, idx->parts);
+        k_part_recs<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, P, fast_c.p, fast_base.p, idx->parts);
         CUDAF(cudaMemcpyAsync(bcount.p, bstart.p, sizeof(int32_t) * NB_cap, cudaMemcpyDeviceToDevice, st));  // cursors
         k_buckets<1><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p,
                                             entry_edge.p, nullptr);
