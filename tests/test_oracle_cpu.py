@@ -264,3 +264,43 @@ def test_geodesic_known_answers(og):
     assert np.isnan(og.geodesic_distance("vincenty", 0, 0, 180, 0))  # antipodal: FailedToConvergeError
     # haversine on the mean sphere: a quarter great circle
     assert abs(og.geodesic_distance("haversine", 0, 0, 90, 0) - 6371008.8 * np.pi / 2) < 1e-6
+
+
+def test_oracle_properties_distance_hull_simplify(og, conv):
+    """size-independent properties the domain offers, on the oracle itself: distance is symmetric and zero exactly
+    where intersects holds; the hull of a hull is the hull; simplify keeps end points, keeps everything at
+    epsilon <= 0 and never keeps MORE points at a larger epsilon on a plain linestring"""
+    import shapes
+    from geopolars_b200 import GeoArrowArray, GeometryType
+
+    T = dict(zip(shapes.KINDS, [GeometryType.POINT, GeometryType.MULTIPOINT, GeometryType.LINESTRING,
+                                GeometryType.MULTILINESTRING, GeometryType.POLYGON, GeometryType.MULTIPOLYGON]))
+    rng = np.random.default_rng(21)
+    for ka, kb in [("linestring", "linestring"), ("linestring", "polygon"), ("polygon", "polygon"), ("point", "polygon"), ("point", "linestring")]:
+        ra, rb = shapes.random_rows(rng, ka, 300, span=14.0), shapes.random_rows(rng, kb, 300, span=14.0)
+        a, b = GeoArrowArray.from_shapes(T[ka], ra), GeoArrowArray.from_shapes(T[kb], rb)
+        dab, dba = og.distance_rowwise(conv(a), conv(b)), og.distance_rowwise(conv(b), conv(a))
+        ok = ~np.isnan(dab)
+        assert np.array_equal(np.isnan(dab), np.isnan(dba)) and rel_close(dab[ok], dba[ok], 1e-12)
+        assert (dab[ok] >= 0).all()
+        if ka != "point":  # Point x LineString distance uses geo-types' epsilon-based containment, not Intersects
+            hit = og.intersects_rowwise(conv(a), conv(b))
+            assert np.array_equal(dab[ok] == 0.0, hit[ok])
+    # hull idempotence (vertex order included)
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, shapes.random_rows(rng, "polygon", 300))
+    off1, xy1 = og.convex_hull(conv(polys))
+    hulls = GeoArrowArray.polygons(xy1, off1, np.arange(len(polys) + 1))
+    off2, xy2 = og.convex_hull(conv(hulls))
+    assert np.array_equal(off1, off2) and np.array_equal(xy1, xy2)
+    # simplify
+    lens = rng.integers(2, 60, 400)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    xy = np.cumsum(rng.normal(0, 1, (off[-1], 2)), axis=0)
+    ls = GeoArrowArray.linestrings(xy, off)
+    prev = og.simplify_mask(conv(ls), 0.0)
+    assert prev.all()
+    for eps in (0.1, 0.5, 2.0, 10.0):
+        keep = og.simplify_mask(conv(ls), eps)
+        assert keep[off[:-1]].all() and keep[off[1:] - 1].all()  # end points always survive
+        assert keep.sum() <= prev.sum()
+        prev = keep
