@@ -128,7 +128,8 @@ extern "C" int gpl_simplify(gpl_ctx *ctx, const gpl_array *in, double tolerance,
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nc, 256), (int64_t)kSMs * 16));
         GPL_LAUNCH(ctx, k_rdp_gather, grid, 256, 0, nc, xy, keep.p, pos.p, reinterpret_cast<double2 *>(oxy.p));
     }
-    GPL_LAUNCH(ctx, k_rdp_offsets, (int)ceil_div(n_chains + 1, 256), 256, 0, n_chains, off, pos.p, new_off.p);
+    if (off) GPL_LAUNCH(ctx, k_rdp_offsets, (int)ceil_div(n_chains + 1, 256), 256, 0, n_chains, off, pos.p, new_off.p);
+    else GPL_CUDA(cudaMemsetAsync(new_off.p, 0, sizeof(int64_t), ctx->stream));  // an empty array may carry no offsets buffer
     gpl_array *o = array_new(ctx, in->type);
     o->n_geoms = in->n_geoms, o->n_parts = in->n_parts, o->n_rings = in->n_rings, o->n_coords = h_total;
     o->xy = oxy.take(), o->own_xy = true;
