@@ -763,11 +763,14 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     if (!(px >= xlo && px <= xhi)) return false;
     const int32_t nb = l.nb_flags & 0x00ffffff;
     const bool right = px >= 0.5 * (xlo + xhi);  // which side's list (k_fast_fill uses the same midpoint)
-    const float qx = __double2float_rn(right ? px - xlo : xhi - px), qy = __double2float_rn(py - (double)l.yminf);
-    const float tq = qy * l.inv_hf;
-    // qy < 0 <=> p.y < yminf <= ymin ; tq >= nb + 1 => p.y > ymax : no listed edge can act
-    if (qy < 0.0f || !(tq < (float)(nb + 1))) return false;
-    const int32_t b = min((int32_t)tq, nb - 1);
+    // the bucket comes from the SAME double expression the build used (mono_index / candidate_range): a float
+    // product could land one bucket off near a boundary and silently drop an edge whose end lies in the gap
+    const double yrel = py - (double)l.yminf;
+    const double t = yrel * (double)l.inv_hf;
+    // t < 0 <=> p.y < yminf <= ymin ; t >= nb + 1 => p.y > ymax : no listed edge can act
+    if (t < 0.0 || !(t < (double)(nb + 1))) return false;
+    const int32_t b = min((int32_t)t, nb - 1);
+    const float qx = __double2float_rn(right ? px - xlo : xhi - px), qy = __double2float_rn(yrel);
     const float4 *part = fast + (int64_t)l.bucket_base;
     const float4 *rec = part + (b * 2 + (right ? 0 : 1)) * kFastListRecs;
     const float height = l.inv_hf > 0.0f ? __fdividef((float)nb, l.inv_hf) : 0.0f;  // 2 ulp is plenty: R only feeds bounds with 2x slack
