@@ -364,7 +364,7 @@ def _main(out):
             "kernel_ms": k_mean,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "kernel": "k_pip_query<0>",
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "kernel": "k_pip_stream<LEAN> (+ k_pip_deferred)",
                      "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                      "read_plus_write_GBps": (algo_bytes + 4 * n) / (k_mean * 1e-3) / 1e9},
         "gpu_launches": launches,

@@ -145,17 +145,47 @@ extern "C" int gpl_ctx_create(int device, void *stream, gpl_ctx **out) {
 }
 extern "C" int gpl_ctx_set_stream(gpl_ctx *ctx, void *stream) {
     GPL_REQUIRE(ctx != nullptr, GPL_ERR_INVALID_ARG, "ctx is NULL");
-    if (ctx->owns_stream && ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-        ctx->owns_stream = false;
-    }
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t old = ctx->stream, next = nullptr;
+    const bool owned_old = ctx->owns_stream;
     if (stream) {
-        ctx->stream = (cudaStream_t)stream;
+        next = (cudaStream_t)stream;
     } else {
-        GPL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->owns_stream = true;
+        GPL_CUDA(cudaStreamCreateWithFlags(&next, cudaStreamNonBlocking));
     }
+    if (old && old != next) {
+        // The caching allocator hands blocks back for reuse in STREAM ORDER (a Scratch block returns to the cache
+        // while kernels enqueued on the old stream may still read it) and the join index skips its final
+        // synchronize for the same reason: everything enqueued on the new stream must therefore run after
+        // everything already enqueued on the old one.
+        cudaEvent_t ev = nullptr;
+        GPL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ev, old);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(next, ev, 0) : e1;
+        cudaEventDestroy(ev);
+        if (e2 != cudaSuccess) {
+            if (!stream) cudaStreamDestroy(next);
+            return cuda_fail(e2, "ordering the new stream after the old one", __FILE__, __LINE__);
+        }
+        // a live join index keeps its L2 access-policy window on the context stream: move it along
+        if (ctx->l2_pinned) {
+            cudaStreamAttrValue attr;
+            if (cudaStreamGetAttribute(old, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) {
+                (void)cudaStreamSetAttribute(next, cudaStreamAttributeAccessPolicyWindow, &attr);
+                attr.accessPolicyWindow.num_bytes = 0;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+                (void)cudaStreamSetAttribute(old, cudaStreamAttributeAccessPolicyWindow, &attr);
+            }
+            (void)cudaGetLastError();
+        }
+        if (owned_old) {
+            cudaStreamSynchronize(old);
+            cudaStreamDestroy(old);
+        }
+    }
+    ctx->stream = next;
+    ctx->owns_stream = (stream == nullptr);
     return GPL_OK;
 }
 extern "C" int gpl_ctx_synchronize(gpl_ctx *ctx) {

@@ -480,8 +480,8 @@ __device__ __forceinline__ double range_geodesic(const double2 *__restrict__ xy,
 template <int METHOD>
 __global__ void __launch_bounds__(128) k_geodesic_length(int type, int64_t n_geoms, const double2 *__restrict__ xy,
                                                          const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
-                                                         const int64_t *__restrict__ ring_off, double *__restrict__ out,
-                                                         uint8_t *__restrict__ out_valid) {
+                                                         const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
+                                                         double *__restrict__ out, uint8_t *__restrict__ out_valid) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(128) k_geodesic_length(int type, int64_t n_geo
         default: break;
         }
         s = warp_sum(s);
-        ok = __all_sync(0xffffffffu, ok);
+        ok = __all_sync(0xffffffffu, ok) && bit_get(validity, g);  // a null row stays null (area / length / x / y do the same)
         if (lane == 0) {
             out[g] = ok ? s : nan("");
             out_valid[g] = ok ? 1 : 0;
@@ -535,9 +535,9 @@ extern "C" int gpl_geodesic_length(gpl_ctx *ctx, const gpl_array *in, int method
     GPL_TRY(vb.get(ctx, (size_t)n));
     const double2 *xy = reinterpret_cast<const double2 *>(in->xy);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 4), (int64_t)kSMs * 16));
-    if (method == 0) GPL_LAUNCH(ctx, k_geodesic_length<0>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, dst, vb.p);
-    else if (method == 1) GPL_LAUNCH(ctx, k_geodesic_length<1>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, dst, vb.p);
-    else GPL_LAUNCH(ctx, k_geodesic_length<2>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, dst, vb.p);
+    if (method == 0) GPL_LAUNCH(ctx, k_geodesic_length<0>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, dst, vb.p);
+    else if (method == 1) GPL_LAUNCH(ctx, k_geodesic_length<1>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, dst, vb.p);
+    else GPL_LAUNCH(ctx, k_geodesic_length<2>, grid, 128, 0, in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, dst, vb.p);
     if (out_validity) {
         if (mem == GPL_DEVICE) {
             GPL_TRY(pack_bits(ctx, vb.p, out_validity, n));

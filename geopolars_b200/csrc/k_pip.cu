@@ -9,26 +9,38 @@
 //     (pinned by the 9-point vector at spatial_index.rs:432-484),
 //   * output = (lhs_index, rhs_index) pairs (spatial_index.rs:139-157).
 //
-// B200 design.  The polygon side is small (10 MB) and lives in the 126 MB L2; the point side is a
-// 1.6 GB stream.  Random points make every index access a gather; measurements showed the
-// kernel limited first by divergence, then by L1 wavefronts (one per lane per load instruction), then by the
-// number of 32-byte L2 sectors pulled per point, and finally by issue slots.  The layout and the kernel are
-// built around those limits:
-//   grid cell (arithmetic)  -> ONE 32-byte record = candidate count + the first candidate's x-range and
+// B200 design.  The polygon side is small (10 MB) and lives in the 126 MB L2; the point side is a 1.6 GB
+// stream.  Round 1 walked an edge list for EVERY point (two dependent L2 gathers + ~10 edge rules per point,
+// 20 of 32 lanes active, 0.15 of the HBM roofline).  Round 2 answers most points from a 2-bit raster:
+//
+//   fine cell (arithmetic)  -> 2-bit code from an L2-resident raster (16 cells per 32-bit word):
+//                                0 = outside every polygon                       -> id -1, done
+//                                1 / 2 = strictly inside the coarse cell's candidate #0 / #1 and
+//                                        outside every other polygon              -> id from an 8-byte record, done
+//                                3 = a ring passes through (or near) the cell, or anything else -> WALK
+//   WALK (~13 % of the points on config 2): the point is appended to a per-warp shared-memory queue and the
+//   queue is drained 32 points at a time, so that the edge walk runs with full warps:
+//   coarse cell             -> ONE 32-byte record = candidate count + the first candidate's x-range and
 //                              y-bucket parameters (one 256-bit load)
-//   y-bucket (arithmetic)   -> plain parts: fixed-stride FP32 table, header + edges as 16-byte float records
-//                              (no lookup at all: four 256-bit loads fetch the header and seven edges);
-//                              other parts: (start,end) of a list of 32-byte f64 edge records (one 64-bit load)
+//   y-bucket (arithmetic)   -> plain parts: fixed-stride FP32 table, header + edges as 16-byte float records;
+//                              other parts: (start,end) of a list of 32-byte f64 edge records
 //   edge rule               -> branch-free; an FP32 filter with a rigorous error bound on the fast table, the
 //                              f64 determinant with Shewchuk's stage-A filter elsewhere; whatever a filter
 //                              cannot certify is appended to a list and recomputed exactly by a second kernel.
+//
 // Exactness of the pruning: geo's loop only ever acts on an edge when p.y lies in the edge's closed
 // y-range.  Buckets are assigned with f(y) = clamp(floor((y - ymin) * inv_h)), a monotone
 // non-decreasing function of y in IEEE arithmetic (subtraction, multiplication by a positive constant,
 // floor and clamp are all monotone), and an edge is listed in buckets f(ylo)..f(yhi); hence
 // ylo <= p.y <= yhi implies the edge is in bucket f(p.y): the bucket list is a superset of the edges
 // the reference would act on, and every listed edge is evaluated with the reference's own rule.
-// The same argument covers the grid cells (bbox filter).  No epsilon anywhere.
+// The same argument covers the grid cells (bbox filter).  No epsilon anywhere in the pruning.
+//
+// Exactness of the raster (see "raster" below): a cell keeps a code other than 3 only if no ring segment of ANY
+// part comes within 1e-6 cell widths of it; such a cell lies inside one face of every part's ring arrangement, so
+// one exact test of one representative point (geo's rule, adaptive orient2d) classifies every point that maps to
+// the cell.  Points on or near a boundary always take the walk, i.e. geo's own rule.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,6 +48,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+namespace cg = cooperative_groups;
 
 namespace gpl {
 
@@ -70,7 +83,7 @@ struct __align__(32) PartRec {
 };
 static_assert(sizeof(PartRec) == 32, "PartRec must be one sector");
 
-// grid cell: one sector.  count == 1: `first` is the part id and `lite` its parameters — the common
+// coarse grid cell: one sector.  count == 1: `first` is the part id and `lite` its parameters — the common
 // case costs a single 256-bit load.  count > 1: `first` is the offset of the ascending part-id list in
 // cell_items[], `lite` belongs to the first (lowest) of them.
 struct __align__(32) CellRec {
@@ -93,10 +106,15 @@ struct __align__(32) EdgeRec {  // one L2 sector
     double sx, sy, ex, ey;
 };
 
+// The grid is defined on FINE cells; a coarse cell is a block of 2^rs x 2^rs fine cells (index >> rs), so the
+// two levels nest exactly by construction.
 struct GridParams {
-    double x0, y0, x1, y1;  // union bbox of valid parts
-    double inv_cw, inv_ch;
-    int32_t gx, gy;
+    double x0, y0, x1, y1;  // union bbox of the valid parts (x0 > x1 when there is none)
+    double inv_fw, inv_fh;  // fine cells per coordinate unit; 0 on a degenerate axis
+    int32_t fgx, fgy;       // fine cells per axis = gx << rs, gy << rs
+    int32_t gx, gy;         // coarse cells per axis
+    int32_t rs;             // log2(fine cells per coarse cell and axis)
+    int32_t wpr;            // raster words per fine row = ceil(fgx / 16): 2 bits per cell
 };
 
 }  // namespace gpl
@@ -111,28 +129,106 @@ struct gpl_pip_index {
     size_t slab_bytes = 0;
     gpl::PartRec *parts = nullptr;
     gpl::CellRec *cells = nullptr;    // gx*gy
-    int32_t *cell_overflow = nullptr; // ascending part ids of the cells with more than one candidate
+    int2 *cand01 = nullptr;           // gx*gy: polygon ROW of the cell's candidate #0 / #1 (-1 = none): raster codes 1 / 2
+    uint32_t *raster = nullptr;       // fgy rows x wpr words, 2 bits per fine cell
+    int32_t *cell_overflow = nullptr; // ascending part ids of the cells' candidates
     int2 *bucket_range = nullptr;     // n_buckets: (start, end) into entries[]
     gpl::EdgeRec *entries = nullptr;
     int32_t *entry_ring = nullptr;    // ring index within part (0 = exterior), only if any part has holes
-    float4 *fast = nullptr;           // FP32 fixed-stride bucket table of the plain parts (see FastTable below)
+    float4 *fast = nullptr;           // FP32 fixed-stride bucket table of the plain parts (see "FP32 fast table" below)
     int64_t n_fast = 0;               // 16-byte records in `fast`
     size_t hot_bytes = 0;             // leading part of the slab the L2 persisting window covers (0 = all)
     bool multi = false;               // MULTIPOLYGON: parts[].geom differs from the part id
     bool any_holes = false;
-    bool lean_ok = false;             // every non-empty cell is a single plain FP32-table candidate: k_pip_query<0, LEAN>
+    bool lean_ok = false;             // every valid part is a plain POLYGON with FP32 lists: LEAN walk
     int64_t n_not_fast = 0;           // valid parts without FP32 lists
-    unsigned long long *n_deferred = nullptr;  // device counter inside the slab
+    unsigned long long *n_deferred = nullptr;  // device counters inside the slab: [0] this launch, [1] since the build
     uint32_t *deferred_list = nullptr;         // indices of deferred points (grown on demand)
     uint32_t deferred_cap = 0;
+    size_t prev_l2_limit = 0;         // cudaLimitPersistingL2CacheSize before this index pinned its slab
+    bool l2_limit_saved = false;
     int64_t bytes = 0;
 };
 
 namespace gpl {
 
 // ------------------------------------------------------------------------------------------------
-// index build
+// monotone index functions (see the exactness argument at the top of the file)
 // ------------------------------------------------------------------------------------------------
+// fine cell of v: IEEE subtraction and multiplication by a non-negative constant are monotone, the conversion
+// rounds towards -inf and saturates, min/max clamp: a monotone non-decreasing function of v.  NaN -> 0 (callers
+// reject NaN first).  Build and query use THIS function, and the coarse cell is its value >> rs.
+__device__ __forceinline__ int32_t fine_index(double v, double lo, double inv, int32_t n) {
+    return min(max(__double2int_rd((v - lo) * inv), 0), n - 1);
+}
+// y-bucket of a part (float-valued parameters, double evaluation)
+__device__ __forceinline__ int32_t mono_index(double v, double lo, double inv, int32_t n) {
+    double t = floor((v - lo) * inv);
+    // NaN never reaches here (callers reject points outside the closed bbox first)
+    if (!(t > 0.0)) return 0;
+    if (t >= (double)n) return n - 1;
+    return (int32_t)t;
+}
+__device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// order-preserving encoding of doubles as unsigned integers (atomicMax on the union bbox)
+__device__ __forceinline__ unsigned long long ord_enc(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double ord_dec(unsigned long long u) {
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// index build: two cooperative kernels (count / fill) with one host round trip between them for the
+// data-dependent sizes.  Round 1 issued ~27 small launches and two host syncs per build (0.35 ms, and the part of the
+// step that scaled worst over 8 processes); the phases are the same, separated by grid barriers instead of launches.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBuildThreads = 256;
+constexpr int kMaxBuildCtas = 1024;
+
+enum {  // BuildArgs::acc slots (unsigned long long each, zeroed by the host before the count kernel)
+    ACC_XMIN = 0, ACC_YMIN, ACC_XMAX, ACC_YMAX,  // union bbox, order-preserving encodings (min as max of the complement)
+    ACC_HOLES, ACC_NOT_FAST, ACC_ITEMS, ACC_BUCKETS, ACC_ENTRIES, ACC_FAST, ACC_COUNT
+};
+
+struct BuildArgs {
+    int type;
+    int64_t P, n_geoms;
+    const double2 *xy;
+    const int64_t *geom_off, *part_off, *ring_off;
+    const uint8_t *validity;
+    int slots_x100;
+    int32_t G, rs;
+    int64_t n_cells, NB_cap;
+    // phase 1 (scratch)
+    PartHeader *hdr;
+    int32_t *nb;            // P: buckets per part; scanned in place into the chunk-local exclusive prefix
+    int64_t *partial;       // 4 x kMaxBuildCtas chunk totals of the cooperative scans
+    int32_t *cell_count;    // n_cells + 1
+    int32_t *bcount;        // NB_cap + 1
+    int2 *side_count;       // NB_cap + 1
+    int32_t *fast_c, *fast_slots;  // P + 1
+    unsigned long long *acc;
+    GridParams *gp;
+    // phase 2
+    int64_t n_buckets, n_entries;
+    int32_t *cell_cursor, *bcursor;
+    int64_t *entry_edge;
+    CellRec *cells;
+    int2 *cand01;
+    int32_t *items;
+    PartRec *parts;
+    int2 *bucket_range;
+    EdgeRec *entries;
+    int32_t *entry_ring;
+    float4 *fast;
+    uint32_t *raster;
+    unsigned long long *n_deferred;
+};
+
 __device__ __forceinline__ void part_rings(int type, int64_t part, const int64_t *geom_off, const int64_t *part_off,
                                            int64_t &r0, int64_t &r1) {
     if (type == GPL_POLYGON) {
@@ -141,135 +237,97 @@ __device__ __forceinline__ void part_rings(int type, int64_t part, const int64_t
         r0 = part_off[part], r1 = part_off[part + 1];
     }
 }
-
-// parent geometry of each part (MULTIPOLYGON): geom g owns parts [geom_off[g], geom_off[g+1])
-__global__ void k_part_parent(int64_t n_geoms, const int64_t *__restrict__ geom_off, int32_t *__restrict__ parent) {
-    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= n_geoms) return;
-    for (int64_t p = geom_off[g]; p < geom_off[g + 1]; ++p) parent[p] = (int32_t)g;
+// parent row of a part: POLYGON rows are their own part; MULTIPOLYGON: the row g with geom_off[g] <= p < geom_off[g+1]
+__device__ __forceinline__ int32_t part_parent(const BuildArgs &a, int64_t p) {
+    if (a.type == GPL_POLYGON) return (int32_t)p;
+    int64_t lo = 0, hi = a.n_geoms;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a.geom_off[mid] <= p) lo = mid;
+        else hi = mid;
+    }
+    return (int32_t)lo;
 }
 
-// one warp per part: bbox of the exterior ring, number of buckets
-__global__ void __launch_bounds__(256) k_part_headers(int type, int64_t n_parts, const double2 *__restrict__ xy,
-                                                      const int64_t *__restrict__ geom_off,
-                                                      const int64_t *__restrict__ part_off,
-                                                      const int64_t *__restrict__ ring_off,
-                                                      const uint8_t *__restrict__ validity,
-                                                      const int32_t *__restrict__ parent, PartHeader *__restrict__ parts,
-                                                      int32_t *__restrict__ nb_out, int64_t *__restrict__ any_holes, int slots_x100) {
-    const int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    for (int64_t p = warp; p < n_parts; p += nwarps) {
-        int64_t r0, r1;
-        part_rings(type, p, geom_off, part_off, r0, r1);
-        int32_t g = parent ? parent[p] : (int32_t)p;
-        bool valid = bit_get(validity, g) && r1 > r0;
-        double x0 = inf, y0 = inf, x1 = -inf, y1 = -inf;
-        int64_t n_slots = 0;
-        if (valid) {
-            int64_t c0 = ring_off[r0], c1 = ring_off[r0 + 1];
-            if (c1 <= c0) valid = false;  // empty exterior: Outside for every point
-            for (int64_t c = c0 + lane; c < c1; c += 32) {
-                double2 q = xy[c];
-                x0 = fmin(x0, q.x), y0 = fmin(y0, q.y), x1 = fmax(x1, q.x), y1 = fmax(y1, q.y);
-            }
-            n_slots = ring_off[r1] - ring_off[r0];
-        }
-        x0 = warp_min(x0), y0 = warp_min(y0), x1 = warp_max(x1), y1 = warp_max(y1);
-        if (!(x0 <= x1 && y0 <= y1)) valid = false;  // NaN-only exterior
-        if (lane == 0) {
-            PartHeader h;
-            h.xmin = x0, h.ymin = y0, h.xmax = x1, h.ymax = y1;
-            // ~3 edge slots per y-bucket (slots_x100): on the config-2 stars a bucket lists ~9 of the 64 edges, and
-            // each of its two one-sided lists (FP32 table) ~4.5.
-            int64_t nb = valid ? (n_slots * 100 + slots_x100 - 1) / slots_x100 : 0;
-            if (nb < 1) nb = valid ? 1 : 0;
-            if (nb > 4096) nb = 4096;
-            float yminf = __double2float_rd(y0);
-            double by0 = (double)yminf;
-            double h_ext = y1 - by0;
-            float inv_hf = (valid && h_ext > 0.0 && isfinite(h_ext)) ? __double2float_rn((double)nb / h_ext) : 0.0f;
-            if (!isfinite(inv_hf)) inv_hf = 0.0f;
-            h.by0 = by0;
-            h.inv_h = (double)inv_hf;
-            h.n_buckets = (int32_t)nb;
-            h.bucket_base = 0;
-            h.geom = g;
-            h.flags = (valid ? 2 : 0) | ((r1 - r0 > 1) ? 1 : 0);
-            parts[p] = h;
-            nb_out[p] = (int32_t)nb;
-            if (valid && r1 - r0 > 1) *any_holes = 1;  // benign race: every writer stores the same value
-        }
+// exclusive scan of one value per thread across the CTA (kBuildThreads threads); `total` = CTA sum
+__device__ __forceinline__ int64_t cta_scan_excl(int64_t v, int64_t &total, int64_t *sm /* kBuildThreads/32 + 1 */) {
+    constexpr int NW = kBuildThreads / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-}
-
-// single CTA: union bbox of valid parts + grid parameters
-__global__ void __launch_bounds__(1024) k_grid_params(const PartHeader *__restrict__ parts, int64_t n_parts, int32_t gx,
-                                                      int32_t gy, GridParams *__restrict__ out) {
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double x0 = inf, y0 = inf, x1 = -inf, y1 = -inf;
-    for (int64_t p = threadIdx.x; p < n_parts; p += blockDim.x) {
-        PartHeader h = parts[p];
-        if (h.flags & 2) x0 = fmin(x0, h.xmin), y0 = fmin(y0, h.ymin), x1 = fmax(x1, h.xmax), y1 = fmax(y1, h.ymax);
-    }
-    x0 = warp_min(x0), y0 = warp_min(y0), x1 = warp_max(x1), y1 = warp_max(y1);
-    __shared__ double s[4][32];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) s[0][wid] = x0, s[1][wid] = y0, s[2][wid] = x1, s[3][wid] = y1;
+    if (lane == 31) sm[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        x0 = s[0][lane], y0 = s[1][lane], x1 = s[2][lane], y1 = s[3][lane];
-        x0 = warp_min(x0), y0 = warp_min(y0), x1 = warp_max(x1), y1 = warp_max(y1);
-        if (lane == 0) {
-            GridParams g;
-            g.x0 = x0, g.y0 = y0, g.x1 = x1, g.y1 = y1;
-            double w = x1 - x0, h = y1 - y0;
-            g.inv_cw = (w > 0.0 && isfinite(w)) ? (double)gx / w : 0.0;
-            g.inv_ch = (h > 0.0 && isfinite(h)) ? (double)gy / h : 0.0;
-            if (!isfinite(g.inv_cw)) g.inv_cw = 0.0;
-            if (!isfinite(g.inv_ch)) g.inv_ch = 0.0;
-            g.gx = gx, g.gy = gy;
-            *out = g;
+        const int64_t w = lane < NW ? sm[lane] : 0;
+        int64_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
         }
+        if (lane < NW) sm[lane] = winc - w;
+        if (lane == NW - 1) sm[NW] = winc;
     }
+    __syncthreads();
+    const int64_t excl = sm[wid] + inc - v;
+    total = sm[NW];
+    __syncthreads();  // the scratch is reused by the next call
+    return excl;
+}
+// CTA-local exclusive scan of in[lo,hi) into out[lo,hi) (may alias); returns the chunk total in every thread
+template <typename In, typename Out>
+__device__ int64_t cta_chunk_scan(const In *in, Out *out, int64_t lo, int64_t hi, int64_t *sm) {
+    int64_t carry = 0;
+    for (int64_t base = lo; base < hi; base += kBuildThreads) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < hi ? (int64_t)in[i] : 0;
+        int64_t tot;
+        const int64_t e = cta_scan_excl(v, tot, sm);
+        if (i < hi) out[i] = (Out)(carry + e);
+        carry += tot;
+    }
+    return carry;
+}
+// Cooperative scan, pass A: CTA b scans its chunk [b*L, (b+1)*L) locally and publishes the chunk total.
+template <typename In, typename Out>
+__device__ void grid_scan_local(const In *in, Out *out, int64_t n, int64_t *partial, int64_t *sm) {
+    const int64_t L = ceil_div_dev(n > 0 ? n : 1, gridDim.x);
+    const int64_t lo = min(n, (int64_t)blockIdx.x * L), hi = min(n, lo + L);
+    const int64_t tot = cta_chunk_scan(in, out, lo, hi, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+// pass B (after a grid barrier): exclusive prefix of the chunk totals in shared memory; returns the grand total
+__device__ int64_t grid_scan_prefix(const int64_t *partial, int64_t *sm_prefix /* gridDim.x */, int64_t *sm) {
+    const int64_t total = cta_chunk_scan(partial, sm_prefix, 0, (int64_t)gridDim.x, sm);
+    __syncthreads();  // sm_prefix is read by every thread next
+    return total;
 }
 
-// monotone cell / bucket functions (see the exactness argument at the top of the file)
-__device__ __forceinline__ int32_t mono_index(double v, double lo, double inv, int32_t n) {
-    double t = floor((v - lo) * inv);
-    // NaN never reaches here (callers reject points outside the closed bbox first)
-    if (!(t > 0.0)) return 0;
-    if (t >= (double)n) return n - 1;
-    return (int32_t)t;
+// edge slot c of ring [c0,c1): (c -> c+1), or the implicit closing edge geo's Polygon::new would add
+// for an open ring, or the degenerate edge of a 1-coordinate ring.  Returns false for "no edge".
+__device__ __forceinline__ bool edge_of_slot(const double2 *__restrict__ xy, int64_t c, int64_t c0, int64_t c1, double2 &s,
+                                             double2 &e) {
+    s = xy[c];
+    if (c + 1 < c1) {
+        e = xy[c + 1];
+        return true;
+    }
+    double2 first = xy[c0];
+    if (c1 - c0 == 1) {
+        e = s;
+        return true;
+    }
+    if (first.x == s.x && first.y == s.y) return false;  // ring already closed
+    e = first;
+    return true;
 }
 
-// pass 0 counts, pass 1 fills cell_items (segment per cell): one thread per part walks the cells its
-// bbox overlaps.
-template <int PASS>
-__global__ void k_cells(const PartHeader *__restrict__ parts, int64_t n_parts, const GridParams *__restrict__ gp,
-                        int32_t *__restrict__ count_or_cursor, int32_t *__restrict__ items, int64_t *__restrict__ any_shared_cell) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n_parts) return;
-    PartHeader h = parts[p];
-    if (!(h.flags & 2)) return;
-    GridParams g = *gp;
-    int32_t cx0 = mono_index(h.xmin, g.x0, g.inv_cw, g.gx), cx1 = mono_index(h.xmax, g.x0, g.inv_cw, g.gx);
-    int32_t cy0 = mono_index(h.ymin, g.y0, g.inv_ch, g.gy), cy1 = mono_index(h.ymax, g.y0, g.inv_ch, g.gy);
-    for (int32_t cy = cy0; cy <= cy1; ++cy)
-        for (int32_t cx = cx0; cx <= cx1; ++cx) {
-            int64_t c = (int64_t)cy * g.gx + cx;
-            if (PASS == 0) {
-                if (atomicAdd(&count_or_cursor[c], 1) > 0) *any_shared_cell = 1;  // a cell with several candidates exists
-            } else {
-                int32_t pos = atomicAdd(&count_or_cursor[c], 1);
-                items[pos] = (int32_t)p;
-            }
-        }
-}
 // the x that separates the two one-sided edge lists of a part: the middle of its FLOAT x-range, formed the same
-// way by the build kernels (here) and by the query kernel (from PartLite)
+// way by the build (here) and by the query kernel (from PartLite)
 __device__ __forceinline__ double fast_split_x(const PartHeader &h) {
     return 0.5 * ((double)__double2float_rd(h.xmin) + (double)__double2float_ru(h.xmax));
 }
@@ -283,54 +341,187 @@ __device__ __forceinline__ PartLite lite_of(const PartHeader &h) {
     l.bucket_base = h.bucket_base;
     return l;
 }
-// sort each cell's candidates ascending (first hit = lowest row; parts of one MultiPolygon row are
-// adjacent) and write the one-sector cell record
-__global__ void k_cell_finish(CellRec *__restrict__ cells, const int32_t *__restrict__ cell_start, int32_t *__restrict__ items,
-                              const PartHeader *__restrict__ parts, const int32_t *__restrict__ fast_c,
-                              const int32_t *__restrict__ fast_base, int64_t n_cells) {
-    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    int32_t a = cell_start[c], b = cell_start[c + 1];
-    for (int32_t i = a + 1; i < b; ++i) {
-        int32_t x = items[i], k = i - 1;
-        while (k >= a && items[k] > x) {
-            items[k + 1] = items[k];
-            --k;
-        }
-        items[k + 1] = x;
-    }
-    CellRec r;
-    r.count = b - a;
-    r.first = (b - a == 1) ? items[a] : a;
-    if (b > a) {
-        r.lite = lite_of(parts[items[a]]);
-        if (b - a == 1 && fast_c[items[a]] > 0) {  // the one-load fast path: parameters of the FP32 table
-            r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
-            r.lite.bucket_base = fast_base[items[a]];
-        }
+// the extent R the FP32 filter's error bounds are formed from — one expression, shared by the eligibility test of
+// the build and by fast_walk
+__device__ __forceinline__ float fast_extent(float xminf, float xmaxf, float inv_hf, int32_t nb) {
+    const float height = inv_hf > 0.0f ? __fdividef((float)nb, inv_hf) : 0.0f;  // 2 ulp is plenty: R only feeds bounds with 2x slack
+    return fmaxf(xmaxf - xminf, height);
+}
+
+__device__ __forceinline__ GridParams grid_from_acc(const BuildArgs &a) {
+    GridParams g;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (a.acc[ACC_XMAX] == 0ULL) {  // no valid part: every point fails the bbox test
+        g.x0 = g.y0 = inf, g.x1 = g.y1 = -inf;
     } else {
-        r.lite.xminf = r.lite.xmaxf = r.lite.yminf = r.lite.inv_hf = 0.0f;
-        r.lite.nb_flags = r.lite.bucket_base = 0;
+        g.x0 = ord_dec(~a.acc[ACC_XMIN]), g.y0 = ord_dec(~a.acc[ACC_YMIN]);
+        g.x1 = ord_dec(a.acc[ACC_XMAX]), g.y1 = ord_dec(a.acc[ACC_YMAX]);
     }
-    cells[c] = r;
+    g.gx = g.gy = a.G, g.rs = a.rs;
+    g.fgx = g.fgy = a.G << a.rs;
+    g.wpr = (g.fgx + 15) >> 4;
+    const double w = g.x1 - g.x0, h = g.y1 - g.y0;
+    g.inv_fw = (w > 0.0 && isfinite(w)) ? (double)g.fgx / w : 0.0;
+    g.inv_fh = (h > 0.0 && isfinite(h)) ? (double)g.fgy / h : 0.0;
+    if (!isfinite(g.inv_fw)) g.inv_fw = 0.0;
+    if (!isfinite(g.inv_fh)) g.inv_fh = 0.0;
+    return g;
 }
-__global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ fast_c,
-                            const int32_t *__restrict__ fast_base, PartRec *__restrict__ recs) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n_parts) return;
-    PartHeader h = parts[p];
-    PartRec r;
-    r.lite = lite_of(h);  // bucket_base: the f64 bucket table (general path, exact kernel)
-    r.geom = h.geom;
-    r.pad = 0;
-    if (fast_c[p] > 0) {  // the FP32 lists of this part, for candidates read through the PartRec (LEAN kernel)
-        r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
-        r.pad = fast_base[p];
+
+// ---- phase S0: per part bbox of the exterior ring, bucket count; union bbox ---------------------------------
+__device__ void ph_headers(const BuildArgs &a, double *sm_box /* 4 x 8 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double ux0 = inf, uy0 = inf, ux1 = -inf, uy1 = -inf;  // this warp's share of the union bbox
+    bool holes_seen = false;
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        int64_t r0, r1;
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
+        const int32_t g = part_parent(a, p);
+        bool valid = bit_get(a.validity, g) && r1 > r0;
+        double x0 = inf, y0 = inf, x1 = -inf, y1 = -inf;
+        int64_t n_slots = 0;
+        if (valid) {
+            const int64_t c0 = a.ring_off[r0], c1 = a.ring_off[r0 + 1];
+            if (c1 <= c0) valid = false;  // empty exterior: Outside for every point
+            for (int64_t c = c0 + lane; c < c1; c += 32) {
+                const double2 q = a.xy[c];
+                x0 = fmin(x0, q.x), y0 = fmin(y0, q.y), x1 = fmax(x1, q.x), y1 = fmax(y1, q.y);
+            }
+            n_slots = a.ring_off[r1] - a.ring_off[r0];
+        }
+        x0 = warp_min(x0), y0 = warp_min(y0), x1 = warp_max(x1), y1 = warp_max(y1);
+        if (!(x0 <= x1 && y0 <= y1)) valid = false;  // NaN-only exterior
+        if (valid) {
+            ux0 = fmin(ux0, x0), uy0 = fmin(uy0, y0), ux1 = fmax(ux1, x1), uy1 = fmax(uy1, y1);
+            holes_seen = holes_seen || (r1 - r0 > 1);
+        }
+        if (lane == 0) {
+            PartHeader h;
+            h.xmin = x0, h.ymin = y0, h.xmax = x1, h.ymax = y1;
+            // ~3 edge slots per y-bucket (slots_x100): on the config-2 stars a bucket lists ~9 of the 64 edges, and
+            // each of its two one-sided lists (FP32 table) ~4.5.
+            int64_t nb = valid ? (n_slots * 100 + a.slots_x100 - 1) / a.slots_x100 : 0;
+            if (nb < 1) nb = valid ? 1 : 0;
+            if (nb > 4096) nb = 4096;
+            const float yminf = __double2float_rd(y0);
+            const double by0 = (double)yminf;
+            const double h_ext = y1 - by0;
+            float inv_hf = (valid && h_ext > 0.0 && isfinite(h_ext)) ? __double2float_rn((double)nb / h_ext) : 0.0f;
+            if (!isfinite(inv_hf)) inv_hf = 0.0f;
+            h.by0 = by0;
+            h.inv_h = (double)inv_hf;
+            h.n_buckets = (int32_t)nb;
+            h.bucket_base = 0;
+            h.geom = g;
+            h.flags = (valid ? 2 : 0) | ((r1 - r0 > 1) ? 1 : 0);
+            a.hdr[p] = h;
+            a.nb[p] = (int32_t)nb;
+        }
     }
-    recs[p] = r;
+    // union bbox: warps -> CTA -> four atomics per CTA (same-address atomics serialise: one per part would cost more
+    // than the whole build)
+    if (lane == 0) sm_box[wid] = ux0, sm_box[8 + wid] = uy0, sm_box[16 + wid] = ux1, sm_box[24 + wid] = uy1;
+    const bool any_h = __syncthreads_or(holes_seen);
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kBuildThreads / 32; ++w)
+            ux0 = fmin(ux0, sm_box[w]), uy0 = fmin(uy0, sm_box[8 + w]), ux1 = fmax(ux1, sm_box[16 + w]), uy1 = fmax(uy1, sm_box[24 + w]);
+        if (ux0 <= ux1 && uy0 <= uy1) {
+            atomicMax(a.acc + ACC_XMIN, ~ord_enc(ux0));
+            atomicMax(a.acc + ACC_YMIN, ~ord_enc(uy0));
+            atomicMax(a.acc + ACC_XMAX, ord_enc(ux1));
+            atomicMax(a.acc + ACC_YMAX, ord_enc(uy1));
+        }
+        if (any_h) a.acc[ACC_HOLES] = 1ULL;  // benign race: every writer stores the same value
+    }
+    __syncthreads();
 }
+
+// ---- coarse cells a part's bbox overlaps: pass 0 counts, pass 1 fills the per-cell candidate lists ---------------
+template <int PASS>
+__device__ void ph_cells(const BuildArgs &a, const GridParams &g) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    unsigned long long mine = 0;
+    for (int64_t p = tid; p < a.P; p += nth) {
+        const PartHeader h = a.hdr[p];
+        if (!(h.flags & 2)) continue;
+        const int32_t cx0 = fine_index(h.xmin, g.x0, g.inv_fw, g.fgx) >> g.rs, cx1 = fine_index(h.xmax, g.x0, g.inv_fw, g.fgx) >> g.rs;
+        const int32_t cy0 = fine_index(h.ymin, g.y0, g.inv_fh, g.fgy) >> g.rs, cy1 = fine_index(h.ymax, g.y0, g.inv_fh, g.fgy) >> g.rs;
+        for (int32_t cy = cy0; cy <= cy1; ++cy)
+            for (int32_t cx = cx0; cx <= cx1; ++cx) {
+                const int64_t c = (int64_t)cy * g.gx + cx;
+                if (PASS == 0) {
+                    atomicAdd(&a.cell_count[c], 1);
+                    ++mine;
+                } else {
+                    const int32_t pos = atomicAdd(&a.cell_cursor[c], 1);
+                    a.items[pos] = (int32_t)p;
+                }
+            }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(a.acc + ACC_ITEMS, mine);
+    }
+}
+
+// ---- y-buckets: one warp per part; pass 0 counts bucket entries, pass 1 writes edge ids (global coord index) ------
+template <int PASS>
+__device__ void ph_buckets(const BuildArgs &a, const int64_t *sm_prefix, int64_t chunk_len) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+    unsigned long long mine = 0;
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        PartHeader h = a.hdr[p];
+        if (PASS == 0) {  // finish the scan of the bucket counts: chunk-local prefix + the prefix of the chunk totals
+            h.bucket_base = a.nb[p] + (int32_t)sm_prefix[p / chunk_len];
+            if (lane == 0) a.hdr[p].bucket_base = h.bucket_base;
+        }
+        if (!(h.flags & 2)) continue;
+        const double xm = fast_split_x(h);
+        int64_t r0, r1;
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t c0 = a.ring_off[r], c1 = a.ring_off[r + 1];
+            for (int64_t c = c0 + lane; c < c1; c += 32) {
+                double2 s, e;
+                if (!edge_of_slot(a.xy, c, c0, c1, s, e)) continue;
+                // an edge with a NaN ordinate never satisfies geo's comparisons: it contributes nothing
+                if (isnan(s.y) || isnan(e.y)) continue;
+                const double ylo = fmin(s.y, e.y), yhi = fmax(s.y, e.y);
+                // holes may stick out of the exterior's bbox: only the part of their y-range inside the
+                // bucketed span [ymin,ymax] can hold a queried p.y (queries are bbox-filtered first)
+                if (yhi < h.ymin || ylo > h.ymax) continue;
+                const int32_t b0 = mono_index(fmax(ylo, h.ymin), h.by0, h.inv_h, h.n_buckets);
+                const int32_t b1 = mono_index(fmin(yhi, h.ymax), h.by0, h.inv_h, h.n_buckets);
+                for (int32_t b = b0; b <= b1; ++b) {
+                    if (PASS == 0) {
+                        atomicAdd(&a.bcount[h.bucket_base + b], 1);
+                        ++mine;
+                        // lengths of the two one-sided lists of the FP32 table (same predicate as ph_fast_fill)
+                        if (fmax(s.x, e.x) >= xm) atomicAdd(&a.side_count[h.bucket_base + b].x, 1);
+                        if (fmin(s.x, e.x) <= xm) atomicAdd(&a.side_count[h.bucket_base + b].y, 1);
+                    } else {
+                        const int32_t pos = atomicAdd(&a.bcursor[h.bucket_base + b], 1);
+                        a.entry_edge[pos] = c;
+                    }
+                }
+            }
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(a.acc + ACC_ENTRIES, mine);
+    }
+}
+
 // ---- FP32 fast table --------------------------------------------------------------------------------
-// The query kernel lives on L2: per point it pulls one cell sector plus its edge records, and it slows down as
+// The walk lives on L2: per point it pulls one cell sector plus its edge records, and it slows down as
 // soon as the records it touches stop fitting in L2 next to the 1.6 GB point stream.  Plain parts (no holes,
 // POLYGON rows) therefore get a second, denser table:
 //   * edges as four FLOATS relative to the part origin O = (xminf, yminf): 16 bytes, two per sector;
@@ -344,55 +535,65 @@ __global__ void k_part_recs(const PartHeader *__restrict__ parts, int64_t n_part
 //   * fixed stride: list (b, side) of a part starts at fast_base + (2b + side) * kFastListRecs records: one
 //     header {count, overflow offset} + kFastListRecs-1 edge slots, unused slots hold an inert sentinel (+inf
 //     ordinates) — no (start,end) lookup, the whole list is one batch of 256-bit loads.  Longer lists
-//     continue in a per-part overflow area addressed from the header (exactly sized: k_buckets counts both
+//     continue in a per-part overflow area addressed from the header (exactly sized: ph_buckets counts both
 //     sides).
-// Measured on config 2 (B200, kernel ms per 100 M points): one list per bucket with stride max+1: 2.57;
-// two lists of 8 records: 2.41 (table 100 MB, L2 hit rate 62 %); of 6 records with exact overflow: 2.03; and
-// with 3 instead of 2 edge slots per bucket (table ~50 MB): 1.95.  4-record lists: 2.02.
 // The floats only feed a FILTER with a rigorous error bound (fast_edge_rule); anything it cannot certify is
-// re-evaluated from the f64 records by the exact kernel.  kFastBit lives in PartLite::nb_flags of the CellRec
-// of a single-candidate cell.
+// re-evaluated from the f64 records by the exact kernel.  kFastBit lives in PartLite::nb_flags.
 
 // per part: eligibility and its number of 16-byte records (main lists + overflow)
-__global__ void k_fast_plan(int type, const PartHeader *__restrict__ parts, int64_t n_parts, const int32_t *__restrict__ bcount,
-                            const int2 *__restrict__ side_count, int32_t *__restrict__ fast_c, int32_t *__restrict__ fast_slots,
-                            unsigned long long *__restrict__ n_not_fast) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n_parts) return;
-    PartHeader h = parts[p];
-    int32_t c = 0, slots = 0;
-    if (type == GPL_POLYGON && (h.flags & 2) && !(h.flags & 1)) {
-        int32_t mx = 0, ovf = 0;
-        for (int32_t b = 0; b < h.n_buckets; ++b) {
-            mx = max(mx, bcount[h.bucket_base + b]);
-            const int2 sc = side_count[h.bucket_base + b];
-            ovf += ((max(sc.x - (kFastListRecs - 1), 0) + 1) & ~1) + ((max(sc.y - (kFastListRecs - 1), 0) + 1) & ~1);
+__device__ void ph_fast_plan(const BuildArgs &a) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    unsigned long long slots_sum = 0, not_fast = 0;
+    for (int64_t p = tid; p < a.P; p += nth) {
+        const PartHeader h = a.hdr[p];
+        int32_t c = 0, slots = 0;
+        if (a.type == GPL_POLYGON && (h.flags & 2) && !(h.flags & 1)) {
+            int32_t mx = 0, ovf = 0;
+            for (int32_t b = 0; b < h.n_buckets; ++b) {
+                mx = max(mx, a.bcount[h.bucket_base + b]);
+                const int2 sc = a.side_count[h.bucket_base + b];
+                ovf += ((max(sc.x - (kFastListRecs - 1), 0) + 1) & ~1) + ((max(sc.y - (kFastListRecs - 1), 0) + 1) & ~1);
+            }
+            // The filter's bounds eta = 2^-20 R and B ~ 2^-16 R^2 are formed in FLOAT: they must neither underflow
+            // (R^2 subnormal: the relative-error argument of fast_edge_rule no longer holds) nor overflow (B = inf
+            // defers every point).  Parts outside 2^-50 <= R <= 2^50 keep the f64 walk.
+            const PartLite l = lite_of(h);
+            const float R = fast_extent(l.xminf, l.xmaxf, l.inv_hf, h.n_buckets);
+            const bool scale_ok = R >= 8.8817841970012523e-16f && R <= 1.125899906842624e15f;
+            if (mx <= kFastMaxCount && scale_ok) {
+                c = kFastListRecs;
+                slots = h.n_buckets * 2 * kFastListRecs + ovf;
+            }
         }
-        if (mx <= kFastMaxCount) {
-            c = kFastListRecs;
-            slots = h.n_buckets * 2 * kFastListRecs + ovf;
-        }
+        if ((h.flags & 2) && c == 0) ++not_fast;  // a valid part the FP32 table cannot hold
+        a.fast_c[p] = c;
+        a.fast_slots[p] = slots;
+        slots_sum += (unsigned long long)slots;
     }
-    if ((h.flags & 2) && c == 0) atomicAdd(n_not_fast, 1ULL);  // a valid part the FP32 table cannot hold
-    fast_c[p] = c;
-    fast_slots[p] = slots;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        slots_sum += __shfl_down_sync(0xffffffffu, slots_sum, o);
+        not_fast += __shfl_down_sync(0xffffffffu, not_fast, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (slots_sum) atomicAdd(a.acc + ACC_FAST, slots_sum);
+        if (not_fast) atomicAdd(a.acc + ACC_NOT_FAST, not_fast);
+    }
 }
-// one warp per part: both lists of every bucket (header, float edges, sentinels) and the overflow area
-__global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict__ parts, int64_t n_parts,
-                                                   const int32_t *__restrict__ fast_c, const int32_t *__restrict__ fast_base,
-                                                   const int32_t *__restrict__ bstart, const EdgeRec *__restrict__ entries,
-                                                   float4 *__restrict__ fast) {
+// one warp per part: both lists of every bucket (header, float edges, sentinels) and the overflow area.
+// fast_base[] = a.fast_slots scanned in place.
+__device__ void ph_fast_fill(const BuildArgs &a, const int32_t *__restrict__ bstart) {
     const int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
     const float inf = __int_as_float(0x7f800000);
     const float4 sentinel = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
-    for (int64_t p = warp; p < n_parts; p += nwarps) {
-        if (fast_c[p] == 0) continue;
-        const PartHeader h = parts[p];
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        if (a.fast_c[p] == 0) continue;
+        const PartHeader h = a.hdr[p];
         const double ox = (double)__double2float_rd(h.xmin), mx = (double)__double2float_ru(h.xmax), oy = h.by0;
         const double xm = fast_split_x(h);  // == 0.5 * (ox + mx); the query kernel forms it from PartLite
-        float4 *base = fast + (int64_t)fast_base[p];
+        float4 *base = a.fast + (int64_t)a.fast_slots[p];
         int32_t ovf = h.n_buckets * 2 * kFastListRecs;  // next free overflow record (relative to base, always even)
         for (int32_t b = 0; b < h.n_buckets; ++b) {
             const int32_t e0 = bstart[h.bucket_base + b], n = bstart[h.bucket_base + b + 1] - e0;
@@ -404,7 +605,7 @@ __global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict_
                     bool sel = false;
                     EdgeRec ed{0.0, 0.0, 0.0, 0.0};
                     if (j < n) {
-                        ed = entries[e0 + j];
+                        ed = a.entries[e0 + j];
                         sel = side == 0 ? fmax(ed.sx, ed.ex) >= xm : fmin(ed.sx, ed.ex) <= xm;
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, sel);
@@ -431,187 +632,97 @@ __global__ void __launch_bounds__(256) k_fast_fill(const PartHeader *__restrict_
     }
 }
 
-__global__ void k_bucket_ranges(const int32_t *__restrict__ bstart, int2 *__restrict__ ranges, int64_t n) {
-    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (b < n) ranges[b] = make_int2(bstart[b], bstart[b + 1]);
-}
-
-// edge slot c of ring [c0,c1): (c -> c+1), or the implicit closing edge geo's Polygon::new would add
-// for an open ring, or the degenerate edge of a 1-coordinate ring.  Returns false for "no edge".
-__device__ __forceinline__ bool edge_of_slot(const double2 *__restrict__ xy, int64_t c, int64_t c0, int64_t c1, double2 &s,
-                                             double2 &e) {
-    s = xy[c];
-    if (c + 1 < c1) {
-        e = xy[c + 1];
-        return true;
-    }
-    double2 first = xy[c0];
-    if (c1 - c0 == 1) {
-        e = s;
-        return true;
-    }
-    if (first.x == s.x && first.y == s.y) return false;  // ring already closed
-    e = first;
-    return true;
-}
-
-// one warp per part; pass 0 counts bucket entries, pass 1 writes edge ids (global coord index)
-template <int PASS>
-__global__ void __launch_bounds__(256) k_buckets(int type, int64_t n_parts, const double2 *__restrict__ xy,
-                                                 const int64_t *__restrict__ geom_off,
-                                                 const int64_t *__restrict__ part_off,
-                                                 const int64_t *__restrict__ ring_off,
-                                                 const PartHeader *__restrict__ parts,
-                                                 int32_t *__restrict__ count_or_cursor, int64_t *__restrict__ entry_edge,
-                                                 int2 *__restrict__ side_count) {
-    const int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < n_parts; p += nwarps) {
-        PartHeader h = parts[p];
-        if (!(h.flags & 2)) continue;
-        const double xm = fast_split_x(h);
-        int64_t r0, r1;
-        part_rings(type, p, geom_off, part_off, r0, r1);
-        for (int64_t r = r0; r < r1; ++r) {
-            int64_t c0 = ring_off[r], c1 = ring_off[r + 1];
-            for (int64_t c = c0 + lane; c < c1; c += 32) {
-                double2 s, e;
-                if (!edge_of_slot(xy, c, c0, c1, s, e)) continue;
-                // an edge with a NaN ordinate never satisfies geo's comparisons: it contributes nothing
-                if (isnan(s.y) || isnan(e.y)) continue;
-                double ylo = fmin(s.y, e.y), yhi = fmax(s.y, e.y);
-                // holes may stick out of the exterior's bbox: only the part of their y-range inside the
-                // bucketed span [ymin,ymax] can hold a queried p.y (queries are bbox-filtered first)
-                if (yhi < h.ymin || ylo > h.ymax) continue;
-                int32_t b0 = mono_index(fmax(ylo, h.ymin), h.by0, h.inv_h, h.n_buckets);
-                int32_t b1 = mono_index(fmin(yhi, h.ymax), h.by0, h.inv_h, h.n_buckets);
-                for (int32_t b = b0; b <= b1; ++b) {
-                    if (PASS == 0) {
-                        atomicAdd(&count_or_cursor[h.bucket_base + b], 1);
-                        // lengths of the two one-sided lists of the FP32 table (same predicate as k_fast_fill)
-                        if (fmax(s.x, e.x) >= xm) atomicAdd(&side_count[h.bucket_base + b].x, 1);
-                        if (fmin(s.x, e.x) <= xm) atomicAdd(&side_count[h.bucket_base + b].y, 1);
-                    } else {
-                        int32_t pos = atomicAdd(&count_or_cursor[h.bucket_base + b], 1);
-                        entry_edge[pos] = c;
-                    }
-                }
-            }
-        }
-    }
-}
-
-__global__ void k_set_bucket_base(PartHeader *__restrict__ parts, const int32_t *__restrict__ base, int64_t n_parts) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p < n_parts) parts[p].bucket_base = base[p];
-}
-
 // one thread per segment: insertion sort (lists are a handful of items) — makes cell candidate lists
 // ascending by part id and bucket lists ascending by edge id (=> grouped by ring, deterministic).
 template <typename T>
-__global__ void k_sort_segments(T *__restrict__ items, const int32_t *__restrict__ seg_start, int64_t n_seg) {
-    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    int32_t a = seg_start[s], b = seg_start[s + 1];
-    for (int32_t i = a + 1; i < b; ++i) {
-        T v = items[i];
-        int32_t j = i - 1;
-        while (j >= a && items[j] > v) {
-            items[j + 1] = items[j];
-            --j;
+__device__ void ph_sort_segments(T *__restrict__ items, const int32_t *__restrict__ seg_start, int64_t n_seg) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    for (int64_t s = tid; s < n_seg; s += nth) {
+        const int32_t a = seg_start[s], b = seg_start[s + 1];
+        for (int32_t i = a + 1; i < b; ++i) {
+            const T v = items[i];
+            int32_t j = i - 1;
+            while (j >= a && items[j] > v) {
+                items[j + 1] = items[j];
+                --j;
+            }
+            items[j + 1] = v;
         }
-        items[j + 1] = v;
     }
 }
 
-// materialise sorted edge ids into 32-byte records (+ ring index within the part when holes exist)
-__global__ void k_materialise(int type, int64_t n_parts, const double2 *__restrict__ xy, const int64_t *__restrict__ geom_off,
-                              const int64_t *__restrict__ part_off, const int64_t *__restrict__ ring_off,
-                              const PartHeader *__restrict__ parts, const int32_t *__restrict__ bucket_start,
-                              const int64_t *__restrict__ entry_edge, EdgeRec *__restrict__ entries,
-                              int32_t *__restrict__ entry_ring) {
-    // one warp per part, lanes over the part's entries
+// the one-sector record of every coarse cell + the rows of its first two candidates (raster codes 1 / 2)
+__device__ void ph_cell_finish(const BuildArgs &a, const int32_t *__restrict__ cell_start) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    for (int64_t c = tid; c < a.n_cells; c += nth) {
+        const int32_t s = cell_start[c], e = cell_start[c + 1];
+        CellRec r;
+        r.count = e - s;
+        r.first = (e - s == 1) ? a.items[s] : s;
+        int2 cand = make_int2(-1, -1);
+        if (e > s) {
+            const int32_t p0 = a.items[s];
+            r.lite = lite_of(a.hdr[p0]);
+            if (e - s == 1 && a.fast_c[p0] > 0) {  // the one-load fast path: parameters of the FP32 table
+                r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
+                r.lite.bucket_base = a.fast_slots[p0];
+            }
+            cand.x = a.hdr[p0].geom;
+            if (e - s > 1) cand.y = a.hdr[a.items[s + 1]].geom;
+        } else {
+            r.lite.xminf = r.lite.xmaxf = r.lite.yminf = r.lite.inv_hf = 0.0f;
+            r.lite.nb_flags = r.lite.bucket_base = 0;
+        }
+        a.cells[c] = r;
+        a.cand01[c] = cand;
+    }
+}
+__device__ void ph_part_recs(const BuildArgs &a) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    for (int64_t p = tid; p < a.P; p += nth) {
+        const PartHeader h = a.hdr[p];
+        PartRec r;
+        r.lite = lite_of(h);  // bucket_base: the f64 bucket table (general path, exact kernel)
+        r.geom = h.geom;
+        r.pad = 0;
+        if (a.fast_c[p] > 0) {  // the FP32 lists of this part, for candidates read through the PartRec (LEAN walk)
+            r.lite.nb_flags |= kFastBit | ((kFastListRecs / 2) << kFastCShift);
+            r.pad = a.fast_slots[p];
+        }
+        a.parts[p] = r;
+    }
+}
+// materialise sorted edge ids into 32-byte records (+ ring index within the part when holes exist): one warp per
+// part, lanes over the part's entries
+__device__ void ph_materialise(const BuildArgs &a, const int32_t *__restrict__ bstart) {
     const int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < n_parts; p += nwarps) {
-        PartHeader h = parts[p];
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        const PartHeader h = a.hdr[p];
         if (!(h.flags & 2)) continue;
         int64_t r0, r1;
-        part_rings(type, p, geom_off, part_off, r0, r1);
-        int32_t e0 = bucket_start[h.bucket_base], e1 = bucket_start[h.bucket_base + h.n_buckets];
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
+        const int32_t e0 = bstart[h.bucket_base], e1 = bstart[h.bucket_base + h.n_buckets];
         for (int32_t k = e0 + lane; k < e1; k += 32) {
-            int64_t c = entry_edge[k];
+            const int64_t c = a.entry_edge[k];
             // ring of coordinate c: rings of a part are few; linear search from the exterior
             int64_t r = r0;
-            while (r + 1 < r1 && ring_off[r + 1] <= c) ++r;
+            while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
             double2 s, e;
-            edge_of_slot(xy, c, ring_off[r], ring_off[r + 1], s, e);
+            edge_of_slot(a.xy, c, a.ring_off[r], a.ring_off[r + 1], s, e);
             EdgeRec rec;
             rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
-            entries[k] = rec;
-            if (entry_ring) entry_ring[k] = (int32_t)(r - r0);
+            a.entries[k] = rec;
+            if (a.entry_ring) a.entry_ring[k] = (int32_t)(r - r0);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// the query kernel
+// exact rule (shared by the raster classification, the deferred kernel and the pair mode)
 // ------------------------------------------------------------------------------------------------
-struct IndexView {
-    const CellRec *cells;
-    const int32_t *cell_items;
-    const PartRec *parts;
-    const int2 *bucket_range;
-    const EdgeRec *entries;
-    const int32_t *entry_ring;
-    const float4 *fast;
-    int32_t multi;  // polygon side is MULTIPOLYGON: several parts may share a row
-    GridParams grid;
-};
-
-// 256-bit loads (sm_100: LDG.E.256): one instruction, one L1 wavefront per distinct line
-#ifndef GPL_PIP_NOALLOC
-#define GPL_PIP_NOALLOC 0
-#endif
-__device__ __forceinline__ void ld256(const void *p, double &a, double &b, double &c, double &d) {
-#if GPL_PIP_NOALLOC
-    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-#else
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-#endif
-}
-__device__ __forceinline__ void ld256(const void *p, int32_t (&r)[8]) {
-    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p));
-}
-
-// One edge of geo's coord_pos_relative_to_ring loop, evaluated WITHOUT control flow: the orientation
-// determinant and its static filter (Shewchuk stage A) are computed for every listed edge (nine FP64
-// arithmetic ops, six compares) and the up/down rules are predicate arithmetic.  Whenever the filter
-// cannot certify a NON-ZERO sign on an edge that actually straddles p.y — which includes every
-// collinear (possible boundary) configuration — `undecided` is raised and the point is re-evaluated
-// with the exact adaptive predicate and geo's boundary rule (k_pip_deferred / bucket_contains_exact).
-// Probability ~1e-9 per edge on random data, so the hot loop has no branch, no call, no
-// adaptive-precision code.  The winding contribution is identical to geo's for every decided edge.
-__device__ __forceinline__ void edge_rule_fast(double sx, double sy, double ex, double ey, double px, double py, int &wn,
-                                               bool &undecided) {
-    const double dl = (sx - px) * (ey - py);
-    const double dr = (sy - py) * (ex - px);
-    const double det = dl - dr;
-    // three ordinate comparisons decide everything geo's nested ifs decide:
-    //   a = start.y <= p.y, b = end.y <= p.y, c = end.y >= p.y
-    //   upward rule acts   <=> a && c ; counts <=> a && !b (end.y > p.y) && det > 0
-    //   downward rule acts <=> !a && b ; counts <=> det < 0
-    const bool a = sy <= py, b = ey <= py, c = ey >= py;
-    const bool act = a ? c : b;
-    const bool certain = fabs(det) > kCcwA * (fabs(dl) + fabs(dr));  // strict: det == 0 is never "certain"
-    undecided = undecided || (act && !certain);
-    wn += (int)(a && !b && det > 0.0) - (int)(!a && b && det < 0.0);
-}
-// the same rule with the full adaptive predicate (exact sign always)
+// geo's coord_pos_relative_to_ring step with the full adaptive predicate (exact sign always)
 __device__ __forceinline__ void edge_rule_exact(double sx, double sy, double ex, double ey, double px, double py, int &wn,
                                                 bool &boundary) {
     if (sy <= py) {
@@ -655,6 +766,336 @@ static __device__ __noinline__ bool bucket_contains_exact(const EdgeRec *__restr
     }
     ok = ok && (cur == 0 ? (wn != 0) : (wn == 0));
     return ok && !boundary;
+}
+
+// ------------------------------------------------------------------------------------------------
+// raster: 2 bits per fine cell
+// ------------------------------------------------------------------------------------------------
+// Codes: 0 = outside every part; 1 / 2 = strictly inside candidate #0 / #1 of the coarse cell (its ascending
+// part list) and outside every other part; 3 = walk.  All writes are atomicOr, so codes compose: a second
+// "inside" from another part turns 1|2 into 3, a boundary mark turns anything into 3.
+//
+// Why a code other than 3 is exact.  Work in cell units: T(v) = (v - lo) * inv as a REAL map; the computed
+// (v - lo) * inv of a double differs from T(v) by at most 2^-31 cells (two roundings of 2^-53 relative, at most
+// 2^20 fine cells per axis), so every double that maps to cell (c, r) lies in the real rectangle
+// Q(c,r) = T^-1([c - e/2, c + 1 + e/2] x [r - e/2, r + 1 + e/2]) with e = 1e-6.  raster_mark_edge marks every cell
+// whose e-inflated square meets the segment (row by row, with the slack analysed there), for every ring segment of
+// every valid part — including the closing segment geo's Polygon::new adds and 1-coordinate rings.  A cell that is
+// not marked by part P therefore has no point of P's rings in Q(c,r): Q is convex, so it lies in one face of each
+// ring's arrangement, every winding number geo computes is constant on it and no point of it is on a boundary;
+// horizontally adjacent unmarked cells overlap (their Q's share a strip) and lie in the same face.  One exact
+// evaluation of geo's rule at one representative double that maps to the cell classifies every query point that maps
+// to it.  Anything this argument does not cover (degenerate axis, a representative that does not map back, non-finite
+// coordinates, more than two containing candidates) is coded 3.
+__device__ __forceinline__ void raster_or_span(uint32_t *__restrict__ raster, int32_t wpr, int32_t fy, int32_t c0, int32_t c1,
+                                               uint32_t code) {
+    uint32_t *row = raster + (int64_t)fy * wpr;
+    const uint32_t rep = code * 0x55555555u;
+    for (int32_t w = c0 >> 4; w <= (c1 >> 4); ++w) {
+        const int32_t lo = max(c0 - (w << 4), 0), hi = min(c1 - (w << 4), 15);  // inclusive cell range inside word w
+        const uint32_t m = (0xffffffffu >> (2 * (15 - hi))) & (0xffffffffu << (2 * lo));
+        atomicOr(row + w, rep & m);
+    }
+}
+// mark (code 3) every fine cell within 1e-6 cells of the segment s-e.  Returns false when the segment has a
+// non-finite coordinate in cell units (the caller then marks the whole grid).
+__device__ bool raster_mark_edge(uint32_t *__restrict__ raster, const GridParams &g, double2 s, double2 e) {
+    // the arguments of fine_index, as the query kernel computes them
+    const double tsx = (s.x - g.x0) * g.inv_fw, tsy = (s.y - g.y0) * g.inv_fh;
+    const double tex = (e.x - g.x0) * g.inv_fw, tey = (e.y - g.y0) * g.inv_fh;
+    if (!(isfinite(tsx) && isfinite(tsy) && isfinite(tex) && isfinite(tey))) return false;
+    const double eps = 1e-6;
+    const double ylo = fmin(tsy, tey), yhi = fmax(tsy, tey);
+    const int32_t r0 = min(max(__double2int_rd(ylo - eps), 0), g.fgy - 1), r1 = min(max(__double2int_rd(yhi + eps), 0), g.fgy - 1);
+    const double dy = tey - tsy, dx = tex - tsx;
+    // nearly horizontal in cell units: take the whole x-range on each of the (at most 3) rows
+    const bool flat = fabs(dy) < 1e-3;
+    const double inv_dy = flat ? 0.0 : 1.0 / dy;
+    for (int32_t r = r0; r <= r1; ++r) {
+        double xa, xb;
+        if (flat) {
+            xa = fmin(tsx, tex), xb = fmax(tsx, tex);
+        } else {
+            // parameter range of the segment inside the slab [r - eps, r + 1 + eps].  Errors: the endpoints are within
+            // 2^-30 of their true images and so is dy, i.e. lambda is off by at most 4 * 2^-30 / |dy| — 270 times
+            // smaller than the eps / |dy| the slab was widened by; x(lambda) adds a few 2^-32.  The 2e-6 margin below
+            // covers the rest.
+            double l0 = ((double)r - eps - tsy) * inv_dy, l1 = ((double)r + 1.0 + eps - tsy) * inv_dy;
+            if (l0 > l1) {
+                const double t = l0;
+                l0 = l1, l1 = t;
+            }
+            l0 = fmax(l0, 0.0), l1 = fmin(l1, 1.0);
+            if (l0 > l1) continue;  // a clamped border row the segment does not reach (no query point maps there)
+            xa = tsx + l0 * dx, xb = tsx + l1 * dx;
+            if (xa > xb) {
+                const double t = xa;
+                xa = xb, xb = t;
+            }
+        }
+        const int32_t c0 = min(max(__double2int_rd(xa - 2e-6), 0), g.fgx - 1), c1 = min(max(__double2int_rd(xb + 2e-6), 0), g.fgx - 1);
+        raster_or_span(raster, g.wpr, r, c0, c1, 3u);
+    }
+    return true;
+}
+// one warp per part, lanes over the edge slots of its rings
+__device__ void ph_raster_mark(const BuildArgs &a, const GridParams &g) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+    if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;  // degenerate axis: the raster was filled with 3 (fill kernel, T0)
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        const PartHeader h = a.hdr[p];
+        if (!(h.flags & 2)) continue;
+        int64_t r0, r1;
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
+        bool irregular = false;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t c0 = a.ring_off[r], c1 = a.ring_off[r + 1];
+            for (int64_t c = c0 + lane; c < c1; c += 32) {
+                double2 s, e;
+                if (!edge_of_slot(a.xy, c, c0, c1, s, e)) continue;
+                // an edge with a NaN coordinate never satisfies geo's comparisons (NaN ordinate) or never yields a
+                // non-zero / zero orientation (NaN abscissa): it contributes nothing and bounds no face
+                if (isnan(s.x) || isnan(s.y) || isnan(e.x) || isnan(e.y)) continue;
+                if (!raster_mark_edge(a.raster, g, s, e)) irregular = true;
+            }
+        }
+        if (__any_sync(0xffffffffu, irregular)) {  // infinite coordinates: every cell of the grid takes the walk
+            for (int32_t fy = lane; fy < g.fgy; fy += 32) raster_or_span(a.raster, g.wpr, fy, 0, g.fgx - 1, 3u);
+        }
+    }
+}
+// Polygon::contains(rep) for one part from the f64 bucket records (exact)
+__device__ __forceinline__ bool part_contains_exact(const BuildArgs &a, const PartHeader &h, const int32_t *__restrict__ bstart,
+                                                    double px, double py) {
+    if (!(px >= h.xmin && px <= h.xmax && py >= h.ymin && py <= h.ymax)) return false;
+    const int32_t b = mono_index(py, h.by0, h.inv_h, h.n_buckets);
+    const int32_t e0 = bstart[h.bucket_base + b], e1 = bstart[h.bucket_base + b + 1];
+    return bucket_contains_exact(a.entries, a.entry_ring, (h.flags & 1) != 0, e0, e1, px, py);
+}
+// raster code of "strictly inside part `part` only" in coarse cell (cx, cy): 1 / 2 for candidate #0 / #1, else 3
+__device__ __forceinline__ uint32_t raster_rank_code(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
+                                                     int32_t cx, int32_t cy, int32_t part) {
+    const int64_t c = (int64_t)cy * g.gx + cx;
+    const int32_t s = cell_start[c], e = cell_start[c + 1];
+    if (s < e && a.items[s] == part) return 1u;
+    if (s + 1 < e && a.items[s + 1] == part) return 2u;
+    return 3u;
+}
+// Interior fill: one warp per part, lanes over the fine rows of its bbox; each lane walks its row left to right,
+// classifies the first cell of every run of unmarked cells with one exact test and ORs the run's inside code in.
+__device__ void ph_raster_fill(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
+                               const int32_t *__restrict__ bstart) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+    if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;
+    for (int64_t p = warp; p < a.P; p += nwarps) {
+        const PartHeader h = a.hdr[p];
+        if (!(h.flags & 2)) continue;
+        const int32_t fx0 = fine_index(h.xmin, g.x0, g.inv_fw, g.fgx), fx1 = fine_index(h.xmax, g.x0, g.inv_fw, g.fgx);
+        const int32_t fy0 = fine_index(h.ymin, g.y0, g.inv_fh, g.fgy), fy1 = fine_index(h.ymax, g.y0, g.inv_fh, g.fgy);
+        for (int32_t fy = fy0 + lane; fy <= fy1; fy += 32) {
+            const double ry = g.y0 + ((double)fy + 0.5) / g.inv_fh;
+            const bool row_ok = fine_index(ry, g.y0, g.inv_fh, g.fgy) == fy;
+            uint32_t *row = a.raster + (int64_t)fy * g.wpr;
+            bool in_run = false, inside = false;
+            int32_t cur_cc = -1, wcur = fx0 >> 4;
+            uint32_t code = 3u, wmask = 0u, wval = __ldcg(row + wcur);
+            for (int32_t fx = fx0; fx <= fx1; ++fx) {
+                const int32_t w = fx >> 4, sh = (fx & 15) * 2;
+                if (w != wcur) {
+                    if (wmask) atomicOr(row + wcur, wmask);
+                    wmask = 0u, wcur = w, wval = __ldcg(row + w);
+                }
+                if (((wval >> sh) & 3u) == 3u) {  // a ring of some part passes here: the run ends
+                    in_run = false;
+                    continue;
+                }
+                if (!in_run) {
+                    const double rx = g.x0 + ((double)fx + 0.5) / g.inv_fw;
+                    if (!row_ok || fine_index(rx, g.x0, g.inv_fw, g.fgx) != fx) {  // no representative: walk
+                        wmask |= 3u << sh;
+                        continue;
+                    }
+                    inside = part_contains_exact(a, h, bstart, rx, ry);
+                    in_run = true;
+                }
+                if (inside) {
+                    const int32_t cc = fx >> g.rs;
+                    if (cc != cur_cc) {
+                        cur_cc = cc;
+                        code = raster_rank_code(a, g, cell_start, cc, fy >> g.rs, (int32_t)p);
+                    }
+                    wmask |= code << sh;
+                }
+            }
+            if (wmask) atomicOr(row + wcur, wmask);
+        }
+    }
+}
+
+// ---- the two cooperative kernels --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int64_t sm_scan[kBuildThreads / 32 + 1];
+    __shared__ int64_t sm_prefix[kMaxBuildCtas];
+    __shared__ double sm_box[32];
+    __shared__ GridParams sm_g;
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    // S0: zero the counters the later phases add into; headers + union bbox
+    for (int64_t i = tid; i <= a.n_cells; i += nth) a.cell_count[i] = 0;
+    for (int64_t i = tid; i <= a.NB_cap; i += nth) {
+        a.bcount[i] = 0;
+        a.side_count[i] = make_int2(0, 0);
+    }
+    ph_headers(a, sm_box);
+    grid.sync();
+    // S1: grid parameters (every CTA derives the same values), cell counts, chunk-local scan of the bucket counts
+    if (threadIdx.x == 0) {
+        sm_g = grid_from_acc(a);
+        if (blockIdx.x == 0) *a.gp = sm_g;
+    }
+    __syncthreads();
+    ph_cells<0>(a, sm_g);
+    grid_scan_local(a.nb, a.nb, a.P, a.partial, sm_scan);
+    grid.sync();
+    // S2: bucket bases (finishing the scan), bucket entry counts
+    {
+        const int64_t total = grid_scan_prefix(a.partial, sm_prefix, sm_scan);
+        if (tid == 0) a.acc[ACC_BUCKETS] = (unsigned long long)total;
+        __syncthreads();
+        ph_buckets<0>(a, sm_prefix, ceil_div_dev(a.P > 0 ? a.P : 1, gridDim.x));
+    }
+    grid.sync();
+    // S3: FP32 table plan
+    ph_fast_plan(a);
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int64_t sm_scan[kBuildThreads / 32 + 1];
+    __shared__ int64_t sm_prefix[kMaxBuildCtas];
+    const GridParams g = *a.gp;
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    const bool degenerate = g.inv_fw == 0.0 || g.inv_fh == 0.0;
+    // T0: chunk-local scans (in place): cell counts -> cell starts, bucket counts -> bucket starts, FP32 slots ->
+    // FP32 bases; raster cleared (all 3 on a degenerate grid: every point walks)
+    grid_scan_local(a.cell_count, a.cell_count, a.n_cells, a.partial, sm_scan);
+    grid_scan_local(a.bcount, a.bcount, a.n_buckets, a.partial + kMaxBuildCtas, sm_scan);
+    grid_scan_local(a.fast_slots, a.fast_slots, a.P, a.partial + 2 * kMaxBuildCtas, sm_scan);
+    {
+        const int64_t n_words = (int64_t)g.fgy * g.wpr;
+        const uint32_t fillv = degenerate ? 0xffffffffu : 0u;
+        for (int64_t i = tid; i < n_words; i += nth) a.raster[i] = fillv;
+    }
+    grid.sync();
+    // T1: add the prefixes of the chunk totals; cursors for the fill passes
+    {
+        int64_t total = grid_scan_prefix(a.partial, sm_prefix, sm_scan);
+        int64_t L = ceil_div_dev(a.n_cells > 0 ? a.n_cells : 1, gridDim.x);
+        for (int64_t i = tid; i < a.n_cells; i += nth) {
+            const int32_t v = a.cell_count[i] + (int32_t)sm_prefix[i / L];
+            a.cell_count[i] = v, a.cell_cursor[i] = v;
+        }
+        if (tid == 0) a.cell_count[a.n_cells] = (int32_t)total;
+        __syncthreads();
+        total = grid_scan_prefix(a.partial + kMaxBuildCtas, sm_prefix, sm_scan);
+        L = ceil_div_dev(a.n_buckets > 0 ? a.n_buckets : 1, gridDim.x);
+        for (int64_t i = tid; i < a.n_buckets; i += nth) {
+            const int32_t v = a.bcount[i] + (int32_t)sm_prefix[i / L];
+            a.bcount[i] = v, a.bcursor[i] = v;
+        }
+        if (tid == 0) a.bcount[a.n_buckets] = (int32_t)total;
+        __syncthreads();
+        total = grid_scan_prefix(a.partial + 2 * kMaxBuildCtas, sm_prefix, sm_scan);
+        L = ceil_div_dev(a.P > 0 ? a.P : 1, gridDim.x);
+        for (int64_t i = tid; i < a.P; i += nth) a.fast_slots[i] += (int32_t)sm_prefix[i / L];
+        __syncthreads();
+    }
+    grid.sync();
+    const int32_t *cell_start = a.cell_count, *bstart = a.bcount;
+    // T2: candidate lists of the cells, edge ids of the buckets (atomic cursors; sorted next)
+    ph_cells<1>(a, g);
+    ph_buckets<1>(a, nullptr, 1);
+    grid.sync();
+    // T3: deterministic order
+    ph_sort_segments<int32_t>(a.items, cell_start, a.n_cells);
+    ph_sort_segments<int64_t>(a.entry_edge, bstart, a.n_buckets);
+    grid.sync();
+    // T4: records
+    ph_cell_finish(a, cell_start);
+    ph_part_recs(a);
+    for (int64_t b = tid; b < a.n_buckets; b += nth) a.bucket_range[b] = make_int2(bstart[b], bstart[b + 1]);
+    ph_materialise(a, bstart);
+    ph_raster_mark(a, g);
+    grid.sync();
+    // T5: FP32 lists, raster interior
+    ph_fast_fill(a, bstart);
+    ph_raster_fill(a, g, cell_start, bstart);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the query kernels
+// ------------------------------------------------------------------------------------------------
+struct IndexView {
+    const CellRec *cells;
+    const int32_t *cell_items;
+    const PartRec *parts;
+    const int2 *bucket_range;
+    const EdgeRec *entries;
+    const int32_t *entry_ring;
+    const float4 *fast;
+    const uint32_t *raster;
+    const int2 *cand01;
+    int32_t multi;  // polygon side is MULTIPOLYGON: several parts may share a row
+    GridParams grid;
+};
+__device__ __forceinline__ int64_t coarse_cell(const GridParams &g, double px, double py) {
+    const int32_t cx = fine_index(px, g.x0, g.inv_fw, g.fgx) >> g.rs, cy = fine_index(py, g.y0, g.inv_fh, g.fgy) >> g.rs;
+    return (int64_t)cy * g.gx + cx;
+}
+
+// 256-bit loads (sm_100: LDG.E.256): one instruction, one L1 wavefront per distinct line
+#ifndef GPL_PIP_NOALLOC
+#define GPL_PIP_NOALLOC 0
+#endif
+__device__ __forceinline__ void ld256(const void *p, double &a, double &b, double &c, double &d) {
+#if GPL_PIP_NOALLOC
+    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void ld256(const void *p, int32_t (&r)[8]) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// One edge of geo's coord_pos_relative_to_ring loop, evaluated WITHOUT control flow: the orientation
+// determinant and its static filter (Shewchuk stage A) are computed for every listed edge (nine FP64
+// arithmetic ops, six compares) and the up/down rules are predicate arithmetic.  Whenever the filter
+// cannot certify a NON-ZERO sign on an edge that actually straddles p.y — which includes every
+// collinear (possible boundary) configuration — `undecided` is raised and the point is re-evaluated
+// with the exact adaptive predicate and geo's boundary rule (k_pip_deferred / bucket_contains_exact).
+// Probability ~1e-9 per edge on random data, so the hot loop has no branch, no call, no
+// adaptive-precision code.  The winding contribution is identical to geo's for every decided edge.
+__device__ __forceinline__ void edge_rule_fast(double sx, double sy, double ex, double ey, double px, double py, int &wn,
+                                               bool &undecided) {
+    const double dl = (sx - px) * (ey - py);
+    const double dr = (sy - py) * (ex - px);
+    const double det = dl - dr;
+    // three ordinate comparisons decide everything geo's nested ifs decide:
+    //   a = start.y <= p.y, b = end.y <= p.y, c = end.y >= p.y
+    //   upward rule acts   <=> a && c ; counts <=> a && !b (end.y > p.y) && det > 0
+    //   downward rule acts <=> !a && b ; counts <=> det < 0
+    const bool a = sy <= py, b = ey <= py, c = ey >= py;
+    const bool act = a ? c : b;
+    const bool certain = fabs(det) > kCcwA * (fabs(dl) + fabs(dr));  // strict: det == 0 is never "certain"
+    undecided = undecided || (act && !certain);
+    wn += (int)(a && !b && det > 0.0) - (int)(!a && b && det < 0.0);
 }
 
 #ifndef GPL_PIP_MINB
@@ -741,6 +1182,9 @@ __device__ __forceinline__ bool bucket_walk(const IndexView &ix, int32_t e0, int
 //   determinant: |det - D| <= eta(|u|+|v|+|w|+|z| + 2 eta) + 2^-22(|uv|+|wz|)  (input perturbation plus
 //                three float roundings) <= eta * 8.5 R + 2^-19 R^2 =: B  because |u|,|v|,|w|,|z| <= 2R;
 //                so |det| > B  =>  sign(det) = sign(D) != 0.  B is one constant per (point, part).
+// The relative-error model of the three float roundings needs normal numbers: the build only gives FP32 lists to
+// parts with 2^-50 <= R <= 2^50 (ph_fast_plan), so eta >= 2^-70, B >= 2^-117 and any product below the normal range
+// is far below B (never certified).
 // Anything else raises `undecided`; the point is then recomputed from the f64 records with the exact
 // predicate.  A definite answer is therefore always geo's answer.
 __device__ __forceinline__ void fast_edge_rule(float4 e, float qx, float qy, float eta, float B, int &wn, bool &undecided) {
@@ -762,7 +1206,7 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     const double xlo = (double)l.xminf, xhi = (double)l.xmaxf;
     if (!(px >= xlo && px <= xhi)) return false;
     const int32_t nb = l.nb_flags & 0x00ffffff;
-    const bool right = px >= 0.5 * (xlo + xhi);  // which side's list (k_fast_fill uses the same midpoint)
+    const bool right = px >= 0.5 * (xlo + xhi);  // which side's list (ph_fast_fill uses the same midpoint)
     // the bucket comes from the SAME double expression the build used (mono_index / candidate_range): a float
     // product could land one bucket off near a boundary and silently drop an edge whose end lies in the gap
     const double yrel = py - (double)l.yminf;
@@ -773,13 +1217,12 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
     const float qx = __double2float_rn(right ? px - xlo : xhi - px), qy = __double2float_rn(yrel);
     const float4 *part = fast + (int64_t)l.bucket_base;
     const float4 *rec = part + (b * 2 + (right ? 0 : 1)) * kFastListRecs;
-    const float height = l.inv_hf > 0.0f ? __fdividef((float)nb, l.inv_hf) : 0.0f;  // 2 ulp is plenty: R only feeds bounds with 2x slack
-    const float R = fmaxf(l.xmaxf - l.xminf, height);
+    const float R = fast_extent(l.xminf, l.xmaxf, l.inv_hf, nb);
     const float eta = 9.5367431640625e-07f * R;                          // 2^-20 R
     const float B = 1.01f * (8.5f * eta * R + 1.9073486328125e-06f * R * R);  // eta*8.5R + 2^-19 R^2
     const float inf = __int_as_float(0x7f800000);
     int wn = 0;
-    bool und = false;
+    bool und = !(B >= 1.17549435e-38f);  // defensive: the build never lists a part whose bounds leave the normal range
     // the list: header + (kFastListRecs - 1) edges, issued together; sentinels make the count irrelevant here
     float4 r[kFastListRecs];
 #pragma unroll
@@ -789,41 +1232,137 @@ __device__ __forceinline__ bool fast_walk(const float4 *__restrict__ fast, const
 #pragma unroll
     for (int j = 1; j < kFastListRecs; ++j) fast_edge_rule(r[j], qx, qy, eta, B, wn, und);
     for (int32_t k = kFastListRecs; k <= count; k += 4) {  // longer lists: four more edges per round (2 sectors)
-        float4 t[4];
+        float4 t4[4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            t[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
-            t[2 * j + 1] = t[2 * j];
-            if (k + 2 * j <= count) ld256f(more + k + 2 * j, t[2 * j], t[2 * j + 1]);  // slots past `count` are sentinels
+            t4[2 * j] = make_float4(0.0f, inf, 0.0f, inf);
+            t4[2 * j + 1] = t4[2 * j];
+            if (k + 2 * j <= count) ld256f(more + k + 2 * j, t4[2 * j], t4[2 * j + 1]);  // slots past `count` are sentinels
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) fast_edge_rule(t[j], qx, qy, eta, B, wn, und);
+        for (int j = 0; j < 4; ++j) fast_edge_rule(t4[j], qx, qy, eta, B, wn, und);
     }
     undecided = undecided || und;
     return wn != 0;
 }
 
-// MODE 0: first_id (+ optional count); undecided points get first_id = kDeferred and bump *n_deferred.
-// MODE 1: write every (point, polygon) pair at pair_off[i]; undecided candidates are resolved in place
-//         with the exact predicate (this mode is not the throughput path).
-//
-// One thread per point, 32 consecutive points per warp (coalesced 512-byte read, software-prefetched one
-// grid stride ahead so the HBM latency is off the dependent chain).  Per point:
-//   grid cell (arithmetic) -> CellRec: ONE 256-bit load = candidate count + first candidate's parameters
-//   x-range / y-bucket (arithmetic) -> (start,end) of the edge list: one 64-bit load
-//   edge records: 256-bit loads, four in flight, branch-free rule.
-// Further candidates of the cell (overlapping bboxes) and MULTIPOLYGON rows read one 32-byte PartRec each.
-// No function calls and no adaptive-precision code in MODE 0: the register budget stays at 64 with
-// four CTAs per SM.
+// The walk of ONE point that lies inside the union bbox: coarse cell -> candidates -> edge lists.
+// MODE 0: first (lowest containing row or -1) and cnt; `undecided` = a filter could not certify something: the caller
+//         defers the point to the exact kernel.
+// MODE 1: write every (point, polygon) pair at lhs/rhs[w...]; undecided candidates are resolved in place with the
+//         exact predicate (this mode is not the throughput path).
+// LEAN (MODE 0 only): every part of the index is a plain POLYGON with FP32 lists (the host checks it), so the
+// f64 bucket walk is compiled out and every candidate runs the FP32 walk.  A candidate that would still need the
+// f64 walk is deferred (cannot happen when the host check holds; kept so that the kernel is correct on any index).
+template <int MODE, bool LEAN>
+__device__ __forceinline__ void walk_point(const IndexView &ix, const double2 p, const bool want_count, int32_t &first, int32_t &cnt,
+                                           bool &undecided, uint64_t gi, int64_t w, uint64_t *__restrict__ lhs,
+                                           uint64_t *__restrict__ rhs) {
+    int32_t r[8];
+    ld256(ix.cells + coarse_cell(ix.grid, p.x, p.y), r);
+    const int32_t n_cand = r[0], first_part = r[1];
+    int32_t last_geom = -1;
+    for (int32_t c = 0; c < n_cand; ++c) {
+        int32_t part = first_part, geom;
+        PartLite lite;
+        if (c == 0 && !ix.multi) {
+            unpack_lite(r + 2, lite);
+            if (lite.nb_flags & kFastBit) {  // single plain candidate: FP32 filter over the fast table
+                bool und = false;
+                bool inside = fast_walk(ix.fast, lite, p.x, p.y, und);
+                if (und) {
+                    if (MODE == 0) {
+                        undecided = true;
+                        return;
+                    }
+                    // pair mode: resolve in place from the f64 records
+                    int32_t q[8];
+                    ld256(ix.parts + first_part, q);
+                    PartLite gl;
+                    unpack_lite(q, gl);
+                    int32_t a0, a1;
+                    inside = candidate_range(ix, gl, p.x, p.y, a0, a1) &&
+                             bucket_contains_exact(ix.entries, ix.entry_ring, false, a0, a1, p.x, p.y);
+                }
+                if (inside) {
+                    if (MODE == 1) {
+                        lhs[w] = gi;
+                        rhs[w] = (uint64_t)first_part;
+                        ++w;
+                    } else {
+                        first = first_part;
+                        cnt = 1;
+                    }
+                }
+                return;
+            }
+            if (LEAN && n_cand == 1) {  // a lone candidate without FP32 lists
+                undecided = true;
+                return;
+            }
+        }
+        if (LEAN) {  // every candidate through its FP32 lists; anything else goes to the exact kernel
+            int32_t q[8];
+            const int32_t cand = __ldg(ix.cell_items + first_part + c);
+            ld256(ix.parts + cand, q);
+            PartLite fl;
+            unpack_lite(q, fl);
+            fl.bucket_base = q[7];  // PartRec::pad = base of the part's FP32 lists
+            bool und = !(fl.nb_flags & kFastBit);
+            const bool inside = !und && fast_walk(ix.fast, fl, p.x, p.y, und);
+            if (und) {
+                undecided = true;
+                return;
+            }
+            if (inside) {
+                if (first < 0) first = cand;
+                ++cnt;
+                if (!want_count) return;
+            }
+            continue;
+        }
+        if (c == 0 && !ix.multi) {
+            if (n_cand > 1) part = __ldg(ix.cell_items + first_part);
+            geom = part;
+        } else {
+            if (n_cand > 1) part = __ldg(ix.cell_items + first_part + c);
+            int32_t q[8];
+            ld256(ix.parts + part, q);
+            unpack_lite(q, lite);
+            geom = q[6];
+        }
+        if (geom == last_geom) continue;  // MultiPolygon::contains = any part; count rows once
+        int32_t e0, e1;
+        if (!candidate_range(ix, lite, p.x, p.y, e0, e1)) continue;
+        bool und = false;
+        bool inside = lite.nb_flags < 0 ? bucket_walk<true>(ix, e0, e1, p.x, p.y, und) : bucket_walk<false>(ix, e0, e1, p.x, p.y, und);
+        if (und) {
+            if (MODE == 0) {
+                undecided = true;
+                return;
+            }
+            inside = bucket_contains_exact(ix.entries, ix.entry_ring, lite.nb_flags < 0, e0, e1, p.x, p.y);
+        }
+        if (!inside) continue;
+        last_geom = geom;
+        if (MODE == 1) {
+            lhs[w] = gi;
+            rhs[w] = (uint64_t)geom;
+            ++w;
+        } else {
+            if (first < 0) first = geom;
+            ++cnt;
+            if (!want_count) return;  // only the first hit is wanted
+        }
+    }
+}
+
 #ifndef GPL_PIP_LEAN_MINB
 #define GPL_PIP_LEAN_MINB 4
 #endif
-// LEAN (MODE 0 only): every part of the index is a plain POLYGON with FP32 lists (the host checks it), so the
-// f64 bucket walk is compiled out and further candidates of a cell run the same FP32 walk from their PartRec —
-// 64 instead of 78 registers, four instead of three resident CTAs per SM.  Measured on config 2 (kernel ms per
-// 100 M points): full kernel 1.93, LEAN at 4 CTAs/SM 1.66, LEAN capped at 47 registers for 5 CTAs/SM (spills) 1.86.  A candidate that would still need
-// the f64 walk is deferred to the exact kernel (cannot happen when the host check holds; kept so that the
-// kernel is correct on any index).
+// Round-1 kernel, kept for MODE 1 (pair lists) and as the A/B baseline (GPL_PIP_LEGACY=1): one thread per point,
+// every point walks.  32 consecutive points per warp (coalesced 512-byte read, software-prefetched one grid stride
+// ahead).
 template <int MODE, bool LEAN = false>
 __global__ void __launch_bounds__(kQueryThreads, LEAN ? GPL_PIP_LEAN_MINB : GPL_PIP_MINB) k_pip_query(const IndexView ix, const double2 *__restrict__ pts,
                                                                            const uint8_t *__restrict__ pts_validity,
@@ -846,127 +1385,9 @@ __global__ void __launch_bounds__(kQueryThreads, LEAN ? GPL_PIP_LEAN_MINB : GPL_
         if (ok && pts_validity) ok = bit_get(pts_validity, i);
         int32_t first = -1, cnt = 0;
         bool undecided = false;
-        int64_t w = MODE == 1 ? pair_off[i] : 0;
-        if (ok) {
-            const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
-            int32_t r[8];
-            ld256(ix.cells + ((int64_t)cy * g.gx + cx), r);
-            const int32_t n_cand = r[0], first_part = r[1];
-            int32_t last_geom = -1;
-            for (int32_t c = 0; c < n_cand; ++c) {
-                int32_t part = first_part, geom;
-                PartLite lite;
-                if (c == 0 && !ix.multi) {
-                    unpack_lite(r + 2, lite);
-                    if (lite.nb_flags & kFastBit) {  // single plain candidate: FP32 filter over the fast table
-                        bool und = false;
-                        bool inside = fast_walk(ix.fast, lite, p.x, p.y, und);
-                        if (und) {
-                            if (MODE == 0) {
-                                undecided = true;
-                                break;
-                            }
-                            // pair mode: resolve in place from the f64 records
-                            int32_t q[8];
-                            ld256(ix.parts + first_part, q);
-                            PartLite gl;
-                            unpack_lite(q, gl);
-                            int32_t a0, a1;
-                            inside = candidate_range(ix, gl, p.x, p.y, a0, a1) &&
-                                     bucket_contains_exact(ix.entries, ix.entry_ring, false, a0, a1, p.x, p.y);
-                        }
-                        if (inside) {
-                            if (MODE == 1) {
-                                lhs[w] = (uint64_t)(point_base + i);
-                                rhs[w] = (uint64_t)first_part;
-                                ++w;
-                            } else {
-                                first = first_part;
-                                cnt = 1;
-                            }
-                        }
-                        break;
-                    }
-                    if (LEAN && n_cand == 1) {  // a lone candidate without FP32 lists
-                        undecided = true;
-                        break;
-                    }
-                    if (LEAN) {  // every candidate through its FP32 lists; anything else goes to the exact kernel
-                        int32_t q[8];
-                        const int32_t cand = __ldg(ix.cell_items + first_part + c);
-                        ld256(ix.parts + cand, q);
-                        PartLite fl;
-                        unpack_lite(q, fl);
-                        fl.bucket_base = q[7];  // PartRec::pad = base of the part's FP32 lists
-                        bool und = !(fl.nb_flags & kFastBit);
-                        const bool inside = !und && fast_walk(ix.fast, fl, p.x, p.y, und);
-                        if (und) {
-                            undecided = true;
-                            break;
-                        }
-                        if (inside) {
-                            if (first < 0) first = cand;
-                            ++cnt;
-                            if (count == nullptr) break;
-                        }
-                        continue;
-                    }
-                    if (n_cand > 1) part = __ldg(ix.cell_items + first_part);
-                    geom = part;
-                } else {
-                    if (LEAN) {  // every candidate through its FP32 lists; anything else goes to the exact kernel
-                        int32_t q[8];
-                        const int32_t cand = __ldg(ix.cell_items + first_part + c);
-                        ld256(ix.parts + cand, q);
-                        PartLite fl;
-                        unpack_lite(q, fl);
-                        fl.bucket_base = q[7];  // PartRec::pad = base of the part's FP32 lists
-                        bool und = !(fl.nb_flags & kFastBit);
-                        const bool inside = !und && fast_walk(ix.fast, fl, p.x, p.y, und);
-                        if (und) {
-                            undecided = true;
-                            break;
-                        }
-                        if (inside) {
-                            if (first < 0) first = cand;
-                            ++cnt;
-                            if (count == nullptr) break;
-                        }
-                        continue;
-                    }
-
-                    if (n_cand > 1) part = __ldg(ix.cell_items + first_part + c);
-                    int32_t q[8];
-                    ld256(ix.parts + part, q);
-                    unpack_lite(q, lite);
-                    geom = q[6];
-                }
-                if (geom == last_geom) continue;  // MultiPolygon::contains = any part; count rows once
-                int32_t e0, e1;
-                if (!candidate_range(ix, lite, p.x, p.y, e0, e1)) continue;
-                bool und = false;
-                bool inside = lite.nb_flags < 0 ? bucket_walk<true>(ix, e0, e1, p.x, p.y, und)
-                                                : bucket_walk<false>(ix, e0, e1, p.x, p.y, und);
-                if (und) {
-                    if (MODE == 0) {
-                        undecided = true;
-                        break;
-                    }
-                    inside = bucket_contains_exact(ix.entries, ix.entry_ring, lite.nb_flags < 0, e0, e1, p.x, p.y);
-                }
-                if (!inside) continue;
-                last_geom = geom;
-                if (MODE == 1) {
-                    lhs[w] = (uint64_t)(point_base + i);
-                    rhs[w] = (uint64_t)geom;
-                    ++w;
-                } else {
-                    if (first < 0) first = geom;
-                    ++cnt;
-                    if (count == nullptr) break;  // only the first hit is wanted
-                }
-            }
-        }
+        if (ok)
+            walk_point<MODE, LEAN>(ix, p, count != nullptr, first, cnt, undecided, (uint64_t)(point_base + i), MODE == 1 ? pair_off[i] : 0, lhs,
+                                   rhs);
         if (MODE == 0) {
             if (undecided) {
                 first = kDeferred;
@@ -979,17 +1400,162 @@ __global__ void __launch_bounds__(kQueryThreads, LEAN ? GPL_PIP_LEAN_MINB : GPL_
     }
 }
 
-// Exact re-evaluation of the points k_pip_query<0> marked kDeferred (those whose filters could not
+// ---- the streaming kernel (MODE 0 of round 2) --------------------------------------------------------------
+// Persistent warps; a warp takes tiles of 128 consecutive points (2 KB, two 256-bit loads per lane, the next tile
+// prefetched into registers).  Per point: closed bbox test, fine cell by arithmetic, ONE 32-bit load of the raster
+// word (four independent loads in flight per lane), then
+//   code 0      -> -1
+//   code 1 / 2  -> the row of the coarse cell's candidate #0 / #1 (one 8-byte load, 80 KB table: L1 hits)
+//   code 3      -> appended to the warp's shared-memory queue (ballot + popc compaction).
+// Whenever the queue holds 32 points the warp walks them (walk_point) with all lanes active and overwrites their ids;
+// the rest is drained at the end.  ids are written as 64-bit stores (two consecutive points per lane).
+constexpr int kTilePts = 128;
+constexpr int kQueueCap = kTilePts + 32;
+constexpr int kStreamWarps = kQueryThreads / 32;
+struct __align__(16) StreamSmem {
+    double2 q_pts[kStreamWarps][kQueueCap];
+    uint32_t q_idx[kStreamWarps][kQueueCap];
+};
+#ifndef GPL_PIP_STREAM_MINB
+#define GPL_PIP_STREAM_MINB 3
+#endif
+__device__ __forceinline__ void ld256s(const double2 *p, double2 &a, double2 &b) {  // read-once stream: evict first
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+template <bool LEAN>
+__global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
+                                                                                  const uint8_t *__restrict__ pts_validity, int64_t n_pts,
+                                                                                  int32_t *__restrict__ first_id, int32_t *__restrict__ count,
+                                                                                  unsigned long long *__restrict__ n_deferred,
+                                                                                  uint32_t *__restrict__ deferred_list, uint32_t list_cap,
+                                                                                  int vec_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+    const GridParams &g = ix.grid;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double2 *q_pts = sm.q_pts[wid];
+    uint32_t *q_idx = sm.q_idx[wid];
+    int qn = 0;  // points waiting in this warp's queue (warp-uniform)
+    const int64_t n_tiles = (n_pts + kTilePts - 1) / kTilePts;
+    const int64_t n_warps = (int64_t)gridDim.x * kStreamWarps;
+    int64_t tile = (int64_t)blockIdx.x * kStreamWarps + wid;
+    const bool want_count = count != nullptr;
+
+    auto walk_queued = [&](int e, bool active) {
+        double2 p = make_double2(0.0, 0.0);
+        uint32_t idx = 0;
+        if (active) p = q_pts[e], idx = q_idx[e];
+        __syncwarp();  // every lane holds its entry before the queue is written again
+        if (active) {
+            int32_t first = -1, cnt = 0;
+            bool undecided = false;
+            walk_point<0, LEAN>(ix, p, want_count, first, cnt, undecided, 0, 0, nullptr, nullptr);
+            if (undecided) {
+                first = kDeferred;
+                const unsigned long long slot = atomicAdd(n_deferred, 1ULL);
+                if (slot < list_cap) deferred_list[slot] = idx;  // chunk-relative index (chunks are < 2^32 points)
+            }
+            first_id[idx] = first;
+            if (want_count) count[idx] = cnt;
+        }
+    };
+
+    // k-th point of a lane inside a tile: pairs of consecutive points, two groups of 64
+    auto slot_of = [&](int k) { return 2 * lane + (k & 1) + (k >> 1) * 64; };
+    double2 nxt[4];
+    auto load_tile = [&](int64_t t, double2 (&dst)[4]) {
+        const int64_t base = t * kTilePts;
+        if (vec_ok && base + kTilePts <= n_pts) {
+            ld256s(pts + base + 2 * lane, dst[0], dst[1]);
+            ld256s(pts + base + 64 + 2 * lane, dst[2], dst[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t i = base + slot_of(k);
+                dst[k] = i < n_pts ? __ldcs(pts + i) : make_double2(0.0, 0.0);
+            }
+        }
+    };
+    if (tile < n_tiles) load_tile(tile, nxt);
+    for (; tile < n_tiles; tile += n_warps) {
+        double2 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = nxt[k];
+        if (tile + n_warps < n_tiles) load_tile(tile + n_warps, nxt);
+        const int64_t base = tile * kTilePts;
+        // stage 1: fine cells and raster words
+        int32_t fx[4], fy[4];
+        uint32_t word[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + slot_of(k);
+            ok[k] = p[k].x >= g.x0 && p[k].x <= g.x1 && p[k].y >= g.y0 && p[k].y <= g.y1;  // false for NaN (empty point)
+            if (i >= n_pts) ok[k] = false;
+            if (ok[k] && pts_validity) ok[k] = bit_get(pts_validity, i);
+            fx[k] = fine_index(p[k].x, g.x0, g.inv_fw, g.fgx), fy[k] = fine_index(p[k].y, g.y0, g.inv_fh, g.fgy);
+            word[k] = ok[k] ? __ldg(ix.raster + (int64_t)fy[k] * g.wpr + (fx[k] >> 4)) : 0u;
+        }
+        // stage 2: codes -> ids
+        int32_t id[4];
+        uint32_t code[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            code[k] = (word[k] >> ((fx[k] & 15) * 2)) & 3u;
+            id[k] = -1;
+            if (code[k] == 1u || code[k] == 2u) {
+                const int2 cand = __ldg(ix.cand01 + (int64_t)(fy[k] >> g.rs) * g.gx + (fx[k] >> g.rs));
+                id[k] = code[k] == 1u ? cand.x : cand.y;
+            }
+        }
+        // stage 3: ids out (the queued ones are overwritten by the walk)
+        if (vec_ok && base + kTilePts <= n_pts) {
+            __stcs(reinterpret_cast<int2 *>(first_id + base) + lane, make_int2(id[0], id[1]));
+            __stcs(reinterpret_cast<int2 *>(first_id + base + 64) + lane, make_int2(id[2], id[3]));
+            if (want_count) {
+                __stcs(reinterpret_cast<int2 *>(count + base) + lane, make_int2(id[0] >= 0, id[1] >= 0));
+                __stcs(reinterpret_cast<int2 *>(count + base + 64) + lane, make_int2(id[2] >= 0, id[3] >= 0));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t i = base + slot_of(k);
+                if (i < n_pts) {
+                    first_id[i] = id[k];
+                    if (want_count) count[i] = id[k] >= 0;
+                }
+            }
+        }
+        // stage 4: queue the walkers
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool q = code[k] == 3u;
+            const unsigned m = __ballot_sync(0xffffffffu, q);
+            if (q) {
+                const int pos = qn + __popc(m & ((1u << lane) - 1u));
+                q_pts[pos] = p[k];
+                q_idx[pos] = (uint32_t)(base + slot_of(k));
+            }
+            qn += __popc(m);
+        }
+        __syncwarp();
+        while (qn >= 32) {
+            qn -= 32;
+            walk_queued(qn + lane, true);
+        }
+    }
+    if (qn > 0) walk_queued(lane, lane < qn);
+}
+
+// Exact re-evaluation of the points the walk marked kDeferred (those whose filters could not
 // certify an ordinate relation or an orientation that mattered: points within ~1e-6 of an edge or of a
 // vertex ordinate, relative to the part size).  Launched after every query; exits at once when the
 // counter is zero.  One thread per deferred point, taken from the list the query kernel appended to; if
 // the list overflowed, the id column is scanned for the marker instead.
 __device__ __forceinline__ void deferred_point(const IndexView &ix, const double2 *__restrict__ pts, int64_t i,
                                                int32_t *__restrict__ first_id, int32_t *__restrict__ count) {
-    const GridParams &g = ix.grid;
     const double2 p = pts[i];
-    const int32_t cx = mono_index(p.x, g.x0, g.inv_cw, g.gx), cy = mono_index(p.y, g.y0, g.inv_ch, g.gy);
-    const CellRec cell = ix.cells[(int64_t)cy * g.gx + cx];
+    const CellRec cell = ix.cells[coarse_cell(ix.grid, p.x, p.y)];
     int32_t first = -1, cnt = 0, last_geom = -1;
     for (int32_t c = 0; c < cell.count; ++c) {
         const int32_t part = cell.count == 1 ? cell.first : ix.cell_items[cell.first + c];
@@ -1008,18 +1574,20 @@ __device__ __forceinline__ void deferred_point(const IndexView &ix, const double
 }
 __global__ void __launch_bounds__(256) k_pip_deferred(const IndexView ix, const double2 *__restrict__ pts, int64_t n_pts,
                                                       int32_t *__restrict__ first_id, int32_t *__restrict__ count,
-                                                      const unsigned long long *__restrict__ n_deferred,
-                                                      const uint32_t *__restrict__ deferred_list, uint32_t list_cap) {
+                                                      unsigned long long *__restrict__ n_deferred,
+                                                      const uint32_t *__restrict__ deferred_list, uint32_t list_cap,
+                                                      unsigned long long *__restrict__ n_deferred_total) {
     const unsigned long long nd = *n_deferred;
     if (nd == 0ULL) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if (nd <= list_cap) {
         for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)nd; k += stride)
             deferred_point(ix, pts, (int64_t)deferred_list[k], first_id, count);
-        return;
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride)
+            if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count);
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride)
-        if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_deferred_total) atomicAdd(n_deferred_total, nd);
 }
 
 // per-polygon hit counts (config 4's all-reduce input).  Counts are privatised per CTA in shared memory
@@ -1061,23 +1629,37 @@ static IndexView view_of(const gpl_pip_index *idx) {
     v.cells = idx->cells, v.cell_items = idx->cell_overflow, v.parts = idx->parts;
     v.bucket_range = idx->bucket_range, v.entries = idx->entries, v.entry_ring = idx->entry_ring;
     v.fast = idx->fast;
+    v.raster = idx->raster, v.cand01 = idx->cand01;
     v.multi = idx->multi ? 1 : 0;
     v.grid = idx->grid;
     return v;
 }
 
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 static int query_grid(int64_t n, bool lean = false) {
     // persistent-style: 148 SMs x resident CTAs, grid-stride over the point stream
-    static const int per_sm_full = []() {
-        const char *e = getenv("GPL_PIP_CTAS_PER_SM");
-        return e ? atoi(e) : 8;
-    }();
-    static const int per_sm_lean = []() {  // two waves of the resident CTAs of the LEAN kernel
-        const char *e = getenv("GPL_PIP_LEAN_CTAS_PER_SM");
-        return e ? atoi(e) : 2 * GPL_PIP_LEAN_MINB;
-    }();
+    static const int per_sm_full = env_int("GPL_PIP_CTAS_PER_SM", 8);
+    static const int per_sm_lean = env_int("GPL_PIP_LEAN_CTAS_PER_SM", 2 * GPL_PIP_LEAN_MINB);  // two waves of the resident CTAs
     const int per_sm = lean ? per_sm_lean : per_sm_full;
     int64_t want = ceil_div(n, kQueryThreads);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
+}
+// streaming kernel: exactly the resident CTAs (persistent warps, one tile of 128 points per warp and iteration)
+template <bool LEAN>
+static int stream_grid(int64_t n) {
+    static const int per_sm = [] {
+        int occ = 0;
+        cudaFuncSetAttribute(k_pip_stream<LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN>, kQueryThreads, sizeof(StreamSmem)) != cudaSuccess || occ < 1) occ = 1;
+        (void)cudaGetLastError();
+        const int cap = env_int("GPL_PIP_STREAM_CTAS_PER_SM", 0);
+        return cap > 0 ? std::min(cap, occ) : occ;
+    }();
+    const int64_t want = ceil_div(ceil_div(n, kTilePts), kStreamWarps);
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
 
@@ -1086,6 +1668,7 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
     if (n == 0) return GPL_OK;
     const double2 *pts = reinterpret_cast<const double2 *>(pts_dev);
     const IndexView v = view_of(idx);
+    static const bool legacy = env_int("GPL_PIP_LEGACY", 0) != 0;  // round-1 kernel: every point walks (A/B measurements)
     // the deferred list holds chunk-relative uint32 indices: process at most 2^31 points per launch pair
     const int64_t kMaxChunk = 1LL << 31;
     for (int64_t lo = 0; lo < n; lo += kMaxChunk) {
@@ -1100,18 +1683,32 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
             mut->deferred_cap = cap;
         }
         GPL_CUDA(cudaMemsetAsync(idx->n_deferred, 0, sizeof(unsigned long long), stream));
-        if (idx->lean_ok)
-            k_pip_query<0, true><<<query_grid(m, true), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr,
-                                                                                m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
-                                                                                nullptr, nullptr, nullptr, lo, idx->n_deferred,
-                                                                                idx->deferred_list, idx->deferred_cap);
-        else
-            k_pip_query<0, false><<<query_grid(m), kQueryThreads, 0, stream>>>(v, pts + lo, validity_dev ? validity_dev + lo / 8 : nullptr,
-                                                                                 m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
-                                                                                 nullptr, nullptr, nullptr, lo, idx->n_deferred,
-                                                                                 idx->deferred_list, idx->deferred_cap);
-        k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, count_dev ? count_dev + lo : nullptr,
-                                                     idx->n_deferred, idx->deferred_list, idx->deferred_cap);
+        const uint8_t *val = validity_dev ? validity_dev + lo / 8 : nullptr;
+        int32_t *cnt = count_dev ? count_dev + lo : nullptr;
+        if (legacy) {
+            if (idx->lean_ok)
+                k_pip_query<0, true><<<query_grid(m, true), kQueryThreads, 0, stream>>>(v, pts + lo, val, m, first_dev + lo, cnt, nullptr, nullptr,
+                                                                                    nullptr, lo, idx->n_deferred, idx->deferred_list,
+                                                                                    idx->deferred_cap);
+            else
+                k_pip_query<0, false><<<query_grid(m), kQueryThreads, 0, stream>>>(v, pts + lo, val, m, first_dev + lo, cnt, nullptr, nullptr,
+                                                                                     nullptr, lo, idx->n_deferred, idx->deferred_list,
+                                                                                     idx->deferred_cap);
+        } else {
+            // 256-bit point loads and 64-bit id stores need 32- / 8-byte aligned columns (cudaMalloc'd ones are)
+            const int vec_ok = ((reinterpret_cast<uintptr_t>(pts + lo) & 31) == 0 && (reinterpret_cast<uintptr_t>(first_dev + lo) & 7) == 0 &&
+                                (cnt == nullptr || (reinterpret_cast<uintptr_t>(cnt) & 7) == 0))
+                                   ? 1
+                                   : 0;
+            if (idx->lean_ok)
+                k_pip_stream<true><<<stream_grid<true>(m), kQueryThreads, sizeof(StreamSmem), stream>>>(
+                    v, pts + lo, val, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok);
+            else
+                k_pip_stream<false><<<stream_grid<false>(m), kQueryThreads, sizeof(StreamSmem), stream>>>(
+                    v, pts + lo, val, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok);
+        }
+        k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap,
+                                                     idx->n_deferred + 1);
         ctx->launches += 2;
     }
     GPL_CUDA(cudaGetLastError());
@@ -1122,22 +1719,25 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
 
 using namespace gpl;
 
-// Keep the index slab resident in the 126 MB L2 while 1.6 GB of points stream past it: mark the slab
+// Keep the hot part of the index slab resident in the 126 MB L2 while 1.6 GB of points stream past it: mark it
 // as a persisting access-policy window on the context stream (the point loads are ld.global.cs,
-// i.e. evict-first).  Best effort: failures only cost performance.
+// i.e. evict-first).  Best effort: failures only cost performance.  The device-wide carve-out is restored and the
+// persisting lines are released when the index that set them is freed.
 static void l2_pin(gpl_pip_index *idx, bool on) {
     gpl_ctx *ctx = idx->ctx;
-    static const bool enabled = []() {
-        const char *e = getenv("GPL_L2_PIN");
-        return !(e && e[0] == '0');
-    }();
+    static const bool enabled = env_int("GPL_L2_PIN", 1) != 0;
     if (!enabled || ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
     if (on) {
         const size_t want = idx->hot_bytes ? idx->hot_bytes : idx->slab_bytes;
         size_t carve = std::min<size_t>(want, ctx->l2_persist_max);
-        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        size_t prev = 0;
+        if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
+            idx->prev_l2_limit = prev;
+            idx->l2_limit_saved = true;
+        }
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::max(carve, prev));
         size_t win = std::min<size_t>(want, ctx->l2_window_max);
         attr.accessPolicyWindow.base_ptr = idx->slab;
         attr.accessPolicyWindow.num_bytes = win;
@@ -1153,6 +1753,12 @@ static void l2_pin(gpl_pip_index *idx, bool on) {
         ctx->l2_pinned = nullptr;
     }
     (void)cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (!on) {
+        // queries of this index may still be running: the reset must not pull the lines from under them
+        (void)cudaStreamSynchronize(ctx->stream);
+        (void)cudaCtxResetPersistingL2Cache();
+        if (idx->l2_limit_saved) (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, idx->prev_l2_limit);
+    }
     (void)cudaGetLastError();
 }
 
@@ -1165,7 +1771,65 @@ extern "C" void gpl_pip_index_free(gpl_pip_index *idx) {
 }
 extern "C" int64_t gpl_pip_index_bytes(const gpl_pip_index *idx) { return idx ? idx->bytes : 0; }
 
+// diagnostic counters: out[0] = points the exact kernel re-evaluated since the index was built (all queries),
+// out[1] = fine cells per axis, out[2] = log2(fine cells per coarse cell and axis), out[3] = raster cells coded 3,
+// out[4] = raster cells coded 1 or 2, out[5] = parts without FP32 lists, out[6] = index bytes, out[7] = coarse cells per axis.
+// Synchronises the context stream.
+namespace gpl {
+__global__ void k_raster_stats(const uint32_t *__restrict__ raster, int64_t n_words, unsigned long long *__restrict__ out) {
+    unsigned long long walk = 0, inside = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = raster[i], lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+        walk += __popc(lo & hi);
+        inside += __popc(lo ^ hi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        walk += __shfl_down_sync(0xffffffffu, walk, o);
+        inside += __shfl_down_sync(0xffffffffu, inside, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, walk);
+        atomicAdd(out + 1, inside);
+    }
+}
+}  // namespace gpl
+extern "C" int gpl_pip_index_stats(gpl_ctx *ctx, const gpl_pip_index *idx, int64_t *out8) {
+    GPL_REQUIRE(ctx && idx && out8, GPL_ERR_INVALID_ARG, "gpl_pip_index_stats: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    Scratch<unsigned long long> tmp;
+    GPL_TRY(tmp.get(ctx, 2));
+    GPL_CUDA(cudaMemsetAsync(tmp.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    const int64_t n_words = (int64_t)idx->grid.fgy * idx->grid.wpr;
+    if (n_words > 0) {
+        k_raster_stats<<<kSMs * 4, 256, 0, ctx->stream>>>(idx->raster, n_words, tmp.p);
+        ctx->launches++;
+    }
+    unsigned long long h[3] = {0, 0, 0};
+    GPL_CUDA(cudaMemcpyAsync(h, tmp.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(h + 2, idx->n_deferred + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    out8[0] = (int64_t)h[2];
+    out8[1] = idx->grid.fgx;
+    out8[2] = idx->grid.rs;
+    out8[3] = (int64_t)h[0];
+    out8[4] = (int64_t)h[1];
+    out8[5] = idx->n_not_fast;
+    out8[6] = idx->bytes;
+    out8[7] = idx->grid.gx;
+    return GPL_OK;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename K>
+static int coop_grid(K kernel) {
+    int occ = 0, dev = 0, sms = kSMs;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBuildThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs;
+    (void)cudaGetLastError();
+    return std::min(kMaxBuildCtas, sms * std::min(occ, 4));  // every CTA must be resident: grid-wide barriers
+}
 
 extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip_index **out) {
     GPL_REQUIRE(ctx && polys && out, GPL_ERR_INVALID_ARG, "gpl_pip_index_build: NULL argument");
@@ -1193,107 +1857,77 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr, __FILE__, __LINE__)); \
     } while (0)
 
-    const double2 *xy = reinterpret_cast<const double2 *>(polys->xy);
     const int64_t Pa = P > 0 ? P : 1;
     cudaStream_t st = ctx->stream;
+    static const int grid_count = coop_grid(k_pip_build_count), grid_fill = coop_grid(k_pip_build_fill);
 
-    // ---- phase 1 (scratch): bboxes, grid, cell counts, bucket counts --------------------------------
-    Scratch<PartHeader> hdr;
-    Scratch<GridParams> gp;
-    Scratch<int32_t> parent, nb, base, cell_count, cell_start, bcount, bstart, fast_c, fast_slots, fast_base;
-    Scratch<int64_t> totals;
-    TRYF(hdr.get(ctx, (size_t)Pa));
-    TRYF(gp.get(ctx, 1));
-    TRYF(nb.get(ctx, (size_t)Pa + 1));
-    TRYF(base.get(ctx, (size_t)Pa + 1));
-    TRYF(totals.get(ctx, 8));
-    const int32_t *parent_p = nullptr;
-    if (type == GPL_MULTIPOLYGON) {
-        TRYF(parent.get(ctx, (size_t)Pa));
-        if (polys->n_geoms > 0) {
-            k_part_parent<<<(int)ceil_div(polys->n_geoms, 256), 256, 0, st>>>(polys->n_geoms, polys->geom_off, parent.p);
-            ctx->launches++;
-        }
-        parent_p = parent.p;
-    }
-    const int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Pa, 8), (int64_t)kSMs * 8));
-    CUDAF(cudaMemsetAsync(totals.p, 0, sizeof(int64_t) * 8, st));
-    // edge slots per y-bucket x 100.  Measured on config 2 (B200, kernel ms): 133: 2.18, 200: 2.03, 300: 1.95,
+    // edge slots per y-bucket x 100.  Measured on config 2 (B200, round-1 kernel ms): 133: 2.18, 200: 2.03, 300: 1.95,
     // 400: 1.98, 500: 2.07 — fewer, longer buckets keep the FP32 table (and the cell grid) inside L2.
     static const int slots_x100 = [] {
-        const char *e = getenv("GPL_PIP_SLOTS_X100");
-        const int v = e ? atoi(e) : 300;
+        const int v = env_int("GPL_PIP_SLOTS_X100", 300);
         return v >= 25 && v <= 6400 ? v : 300;
     }();
-    k_part_headers<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, polys->validity,
-                                          parent_p, hdr.p, nb.p, totals.p + 4, slots_x100);
-    ctx->launches++;
-    CUDAF(cudaGetLastError());
-
-    // grid: about one cell per part, capped so the cell table stays L2-resident
+    // coarse grid: about one cell per part.  Fine grid: 2^rs x 2^rs cells per coarse cell, as fine as a budget of
+    // raster cells allows (2 bits each: 64 M cells = 16 MB, L2-resident next to the FP32 table), at most 2^7, and at
+    // most 2^20 fine cells per axis (the error analysis of the raster assumes it).
     int64_t G = (int64_t)ceil(sqrt((double)Pa));
     if (G < 1) G = 1;
     if (G > 2048) G = 2048;
     const int64_t n_cells = G * G;
-    k_grid_params<<<1, 1024, 0, st>>>(hdr.p, P, (int32_t)G, (int32_t)G, gp.p);
-    ctx->launches++;
+    static const int rs_max = std::min(7, std::max(0, env_int("GPL_PIP_RASTER_LOG2", 6)));
+    static const int64_t raster_budget = (int64_t)std::max(1, env_int("GPL_PIP_RASTER_MCELLS", 64)) << 20;
+    int rs = rs_max;
+    while (rs > 0 && (((G << rs) > (1 << 20)) || ((G << rs) * (G << rs) > raster_budget))) --rs;
 
+    // ---- phase 1 (scratch): bboxes, grid, cell counts, bucket counts, FP32 plan --------------------------------
+    BuildArgs a;
+    memset(&a, 0, sizeof(a));
+    a.type = type, a.P = P, a.n_geoms = polys->n_geoms;
+    a.xy = reinterpret_cast<const double2 *>(polys->xy);
+    a.geom_off = polys->geom_off, a.part_off = polys->part_off, a.ring_off = polys->ring_off, a.validity = polys->validity;
+    a.slots_x100 = slots_x100, a.G = (int32_t)G, a.rs = rs, a.n_cells = n_cells;
+    // sum of n_buckets <= P + n_coords * 100 / slots_x100 + 1 without a host round trip
+    a.NB_cap = Pa + (polys->n_coords * 100) / slots_x100 + 1;
+    Scratch<PartHeader> hdr;
+    Scratch<GridParams> gp;
+    Scratch<int32_t> nb, cell_count, cell_cursor, bcount, bcursor, fast_c, fast_slots;
+    Scratch<int2> side_count;
+    Scratch<int64_t> partial;
+    Scratch<unsigned long long> acc;
+    TRYF(hdr.get(ctx, (size_t)Pa));
+    TRYF(gp.get(ctx, 1));
+    TRYF(nb.get(ctx, (size_t)Pa + 1));
+    TRYF(partial.get(ctx, (size_t)4 * kMaxBuildCtas));
     TRYF(cell_count.get(ctx, (size_t)n_cells + 1));
-    TRYF(cell_start.get(ctx, (size_t)n_cells + 1));
-    CUDAF(cudaMemsetAsync(cell_count.p, 0, sizeof(int32_t) * (n_cells + 1), st));
-    if (P > 0) {
-        k_cells<0><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, nullptr, totals.p + 6);
-        ctx->launches++;
-    }
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, cell_count.p, n_cells, cell_start.p, totals.p)));
-
-    // bucket bases and per-bucket entry counts (sum of n_buckets <= P + n_coords*100/slots_x100 + 1: no host round trip)
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, nb.p, P, base.p, totals.p + 1)));
-    if (P > 0) {
-        k_set_bucket_base<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, base.p, P);
-        ctx->launches++;
-    }
-    const int64_t NB_cap = Pa + (polys->n_coords * 100) / slots_x100 + 1;
-    TRYF(bcount.get(ctx, (size_t)NB_cap + 1));
-    TRYF(bstart.get(ctx, (size_t)NB_cap + 1));
-    CUDAF(cudaMemsetAsync(bcount.p, 0, sizeof(int32_t) * (NB_cap + 1), st));
-    Scratch<int2> side_count;  // per bucket: lengths of its two one-sided lists (FP32 table)
-    TRYF(side_count.get(ctx, (size_t)NB_cap + 1));
-    CUDAF(cudaMemsetAsync(side_count.p, 0, sizeof(int2) * (NB_cap + 1), st));
-    if (P > 0) {
-        k_buckets<0><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p, nullptr,
-                                            side_count.p);
-        ctx->launches++;
-    }
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, bcount.p, NB_cap, bstart.p, totals.p + 2)));
-    // FP32 fast table plan: records per bucket (C) of every eligible part, then their bases
+    TRYF(bcount.get(ctx, (size_t)a.NB_cap + 1));
+    TRYF(side_count.get(ctx, (size_t)a.NB_cap + 1));
     TRYF(fast_c.get(ctx, (size_t)Pa + 1));
     TRYF(fast_slots.get(ctx, (size_t)Pa + 1));
-    TRYF(fast_base.get(ctx, (size_t)Pa + 1));
-    if (P > 0) {
-        k_fast_plan<<<(int)ceil_div(P, 128), 128, 0, st>>>(type, hdr.p, P, bcount.p, side_count.p, fast_c.p, fast_slots.p,
-                                                           reinterpret_cast<unsigned long long *>(totals.p + 5));
+    TRYF(acc.get(ctx, ACC_COUNT));
+    a.hdr = hdr.p, a.gp = gp.p, a.nb = nb.p, a.partial = partial.p, a.cell_count = cell_count.p, a.bcount = bcount.p;
+    a.side_count = side_count.p, a.fast_c = fast_c.p, a.fast_slots = fast_slots.p, a.acc = acc.p;
+    CUDAF(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * ACC_COUNT, st));
+    {
+        void *args[] = {&a};
+        CUDAF(cudaLaunchCooperativeKernel((void *)k_pip_build_count, dim3(grid_count), dim3(kBuildThreads), args, 0, st));
         ctx->launches++;
     }
-    TRYF((exclusive_scan<int32_t, int32_t>(ctx, fast_slots.p, P, fast_base.p, totals.p + 3)));
-
     // the data-dependent sizes + the grid parameters: one small D2H (index build is once per join)
-    int64_t h_tot[7];
-    CUDAF(cudaMemcpyAsync(h_tot, totals.p, sizeof(int64_t) * 7, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_acc[ACC_COUNT];
+    CUDAF(cudaMemcpyAsync(h_acc, acc.p, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
     CUDAF(cudaMemcpyAsync(&idx->grid, gp.p, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
     CUDAF(cudaStreamSynchronize(st));
-    idx->n_overflow = h_tot[0];  // all cell items
-    idx->n_buckets = h_tot[1];
-    idx->n_entries = h_tot[2];
-    idx->n_fast = h_tot[3];
+    idx->n_overflow = (int64_t)h_acc[ACC_ITEMS];  // all cell items
+    idx->n_buckets = (int64_t)h_acc[ACC_BUCKETS];
+    idx->n_entries = (int64_t)h_acc[ACC_ENTRIES];
+    idx->n_fast = (int64_t)h_acc[ACC_FAST];
     if (idx->n_fast >= (1LL << 31) || idx->n_entries >= (1LL << 31) || idx->n_overflow >= (1LL << 31)) {
         set_error("join index too large (%lld edge records, %lld cell items)", (long long)idx->n_entries,
                   (long long)idx->n_overflow);
         return fail(GPL_ERR_UNSUPPORTED);
     }
-    idx->any_holes = h_tot[4] != 0;  // set on the device: ring counts alone cannot tell (an empty polygon next to one with a hole)
-    idx->n_not_fast = h_tot[5];
-    const bool shared_cells = h_tot[6] != 0;
+    idx->any_holes = h_acc[ACC_HOLES] != 0;  // set on the device: ring counts alone cannot tell (an empty polygon next to one with a hole)
+    idx->n_not_fast = (int64_t)h_acc[ACC_NOT_FAST];
     idx->multi = type == GPL_MULTIPOLYGON;
 
     // ---- phase 2: one slab, filled in place ----------------------------------------------------------
@@ -1305,21 +1939,20 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     };
     // hot structures first: the L2-persisting window covers [0, hot_bytes) only, so the f64 records that
     // just the exact kernel reads do not compete for the cache with the tables every point touches
+    const size_t raster_words = (size_t)idx->grid.fgy * (size_t)idx->grid.wpr;
+    const size_t o_raster = carve(sizeof(uint32_t) * (raster_words + 1));
+    const size_t o_cand = carve(sizeof(int2) * n_cells);
     const size_t o_cells = carve(sizeof(CellRec) * n_cells);
     const size_t o_fast = carve(sizeof(float4) * (idx->n_fast + 8));
     const size_t o_parts = carve(sizeof(PartRec) * Pa);
     const size_t o_brange = carve(sizeof(int2) * (idx->n_buckets + 1));
     const size_t o_items = carve(sizeof(int32_t) * (idx->n_overflow + 1));
-    const size_t o_defer = carve(sizeof(unsigned long long));
+    const size_t o_defer = carve(2 * sizeof(unsigned long long));
     const bool all_fast = idx->n_fast > 0 && !idx->multi && !idx->any_holes;
     {
-        static const bool lean_enabled = [] {
-            const char *e = getenv("GPL_PIP_LEAN");
-            return !e || atoi(e) != 0;  // GPL_PIP_LEAN=0 forces the full kernel (A/B measurements)
-        }();
+        static const bool lean_enabled = env_int("GPL_PIP_LEAN", 1) != 0;  // GPL_PIP_LEAN=0 forces the full walk (A/B measurements)
         // POLYGON rows without holes, every valid part has FP32 lists (cells may hold several candidates)
         idx->lean_ok = lean_enabled && all_fast && idx->n_not_fast == 0;
-        (void)shared_cells;
     }
     const size_t hot_mark = off;
     const size_t o_entries = carve(sizeof(EdgeRec) * (idx->n_entries + 1));
@@ -1329,6 +1962,8 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(ctx->alloc(off, &q));
     idx->slab = (uint8_t *)q;
     idx->slab_bytes = off;
+    idx->raster = (uint32_t *)(idx->slab + o_raster);
+    idx->cand01 = (int2 *)(idx->slab + o_cand);
     idx->cells = (CellRec *)(idx->slab + o_cells);
     idx->parts = (PartRec *)(idx->slab + o_parts);
     idx->bucket_range = (int2 *)(idx->slab + o_brange);
@@ -1341,34 +1976,20 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
 
     Scratch<int64_t> entry_edge;
     TRYF(entry_edge.get(ctx, (size_t)idx->n_entries + 1));
-    if (P > 0) {
-        CUDAF(cudaMemcpyAsync(cell_count.p, cell_start.p, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToDevice, st));  // cursors
-        k_cells<1><<<(int)ceil_div(P, 128), 128, 0, st>>>(hdr.p, P, gp.p, cell_count.p, idx->cell_overflow, nullptr);
+    TRYF(cell_cursor.get(ctx, (size_t)n_cells + 1));
+    TRYF(bcursor.get(ctx, (size_t)idx->n_buckets + 1));
+    a.n_buckets = idx->n_buckets, a.n_entries = idx->n_entries;
+    a.cell_cursor = cell_cursor.p, a.bcursor = bcursor.p, a.entry_edge = entry_edge.p;
+    a.cells = idx->cells, a.cand01 = idx->cand01, a.items = idx->cell_overflow, a.parts = idx->parts;
+    a.bucket_range = idx->bucket_range, a.entries = idx->entries, a.entry_ring = idx->entry_ring, a.fast = idx->fast;
+    a.raster = idx->raster, a.n_deferred = idx->n_deferred;
+    CUDAF(cudaMemsetAsync(idx->n_deferred, 0, 2 * sizeof(unsigned long long), st));
+    {
+        void *args[] = {&a};
+        CUDAF(cudaLaunchCooperativeKernel((void *)k_pip_build_fill, dim3(grid_fill), dim3(kBuildThreads), args, 0, st));
         ctx->launches++;
     }
-    k_cell_finish<<<(int)ceil_div(n_cells, 128), 128, 0, st>>>(idx->cells, cell_start.p, idx->cell_overflow, hdr.p, fast_c.p, fast_base.p,
-                                                                n_cells);
-    ctx->launches++;
-    if (idx->n_buckets > 0) {
-        k_bucket_ranges<<<(int)ceil_div(idx->n_buckets, 256), 256, 0, st>>>(bstart.p, idx->bucket_range, idx->n_buckets);
-        ctx->launches++;
-    }
-    if (P > 0) {
-        k_part_recs<<<(int)ceil_div(P, 256), 256, 0, st>>>(hdr.p, P, fast_c.p, fast_base.p, idx->parts);
-        CUDAF(cudaMemcpyAsync(bcount.p, bstart.p, sizeof(int32_t) * NB_cap, cudaMemcpyDeviceToDevice, st));  // cursors
-        k_buckets<1><<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bcount.p,
-                                            entry_edge.p, nullptr);
-        const int64_t nbk = idx->n_buckets > 0 ? idx->n_buckets : 1;
-        k_sort_segments<int64_t><<<(int)ceil_div(nbk, 128), 128, 0, st>>>(entry_edge.p, bstart.p, idx->n_buckets);
-        k_materialise<<<wgrid, 256, 0, st>>>(type, P, xy, polys->geom_off, polys->part_off, polys->ring_off, hdr.p, bstart.p,
-                                             entry_edge.p, idx->entries, idx->entry_ring);
-        if (idx->n_fast > 0) {
-            k_fast_fill<<<wgrid, 256, 0, st>>>(hdr.p, P, fast_c.p, fast_base.p, bstart.p, idx->entries, idx->fast);
-            ctx->launches++;
-        }
-        ctx->launches += 4;
-        CUDAF(cudaGetLastError());
-    }
+    CUDAF(cudaGetLastError());
     // No final synchronize: the scratch buffers above return to the context cache, which only ever hands them
     // to work enqueued later on this same stream (stream-ordered reuse), and every consumer of the index
     // launches on this stream too.
@@ -1549,3 +2170,4 @@ extern "C" int gpl_join_histogram(gpl_ctx *ctx, const int32_t *first_id, int64_t
     GPL_CUDA(cudaGetLastError());
     return GPL_OK;
 }
+

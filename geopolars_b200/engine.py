@@ -453,6 +453,14 @@ class PipIndex:
     def nbytes(self) -> int:
         return int(self.ctx.lib.gpl_pip_index_bytes(self._h))
 
+    def stats(self) -> dict:
+        """diagnostics: exact re-evaluations since the build, raster geometry and code census"""
+        out = np.zeros(8, dtype=np.int64)
+        check(self.ctx.lib.gpl_pip_index_stats(self.ctx._h, self._h, _np_ptr(out)))
+        keys = ("deferred", "fine_cells_per_axis", "raster_log2", "raster_walk_cells", "raster_inside_cells", "parts_not_fast",
+                "bytes", "coarse_cells_per_axis")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def query(self, points_xy: np.ndarray, with_count: bool = False):
         """first containing polygon row per point (-1 = none) [+ number of containing rows]."""
         pts = np.ascontiguousarray(points_xy, dtype=np.float64).reshape(-1, 2)

@@ -136,11 +136,16 @@ class GeoRustSeries:
         return GeoSeries(_device=d, name=self.series.name)
 
     def affine_transform(self, matrix: AffineTransform) -> GeoSeries:
-        """matrix = [a, b, d, e, xoff, yoff] (the shapely order the reference documents,
-        georust/geoseries.py:33): x' = a*x + b*y + xoff, y' = d*x + e*y + yoff."""
+        """The 6 numbers are handed to geo's `AffineTransform` unchanged, exactly as the reference binding does
+        (py-geopolars/src/geo.rs:10-13 passes `[f64; 6]` into `impl Into<AffineTransform>`, whose
+        `From<[T; 6]>` is `new(a, b, xoff, d, e, yoff)`): matrix = [a, b, xoff, d, e, yoff],
+        x' = a*x + b*y + xoff, y' = d*x + e*y + yoff.  The reference's docstring
+        (georust/geoseries.py:33) advertises shapely's order [a, b, d, e, xoff, yoff]; its executable path
+        does not reorder, and parity follows the executable path (pinned by
+        tests/test_gpu_formats.py::test_affine_matrix_order_is_geos)."""
         if len(matrix) != 6:
-            raise ValueError("matrix must have 6 elements [a, b, d, e, xoff, yoff]")
-        a, b, d, e, xoff, yoff = [float(v) for v in matrix]
+            raise ValueError("matrix must have 6 elements [a, b, xoff, d, e, yoff]")
+        a, b, xoff, d, e, yoff = [float(v) for v in matrix]
         return self._wrap(E.affine_transform(self._d(), (a, b, xoff, d, e, yoff)))
 
     @property

@@ -232,6 +232,11 @@ int gpl_explode(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
 int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polygons, gpl_pip_index **out);
 void gpl_pip_index_free(gpl_pip_index *idx);
 int64_t gpl_pip_index_bytes(const gpl_pip_index *idx);
+/* diagnostic counters (synchronises the context stream): out8[0] = points the exact kernel re-evaluated since the
+ * index was built, [1] = fine raster cells per axis, [2] = log2(fine cells per coarse cell and axis),
+ * [3] = raster cells coded "walk", [4] = raster cells coded "inside", [5] = parts without FP32 lists,
+ * [6] = index bytes, [7] = coarse cells per axis. */
+int gpl_pip_index_stats(gpl_ctx *ctx, const gpl_pip_index *idx, int64_t *out8);
 /* spatial_join(points, polygons, Inner) candidate+exact test (spatial_index.rs:74-143):
  * first_id[p] = lowest polygon row containing point p, or -1; count[p] (may be NULL) = number of
  * containing rows.  points: xy interleaved, n points, in `mem`. */

@@ -128,7 +128,7 @@ def test_geoseries_accessor_surface(ctx):
     assert len(geo.explode()) >= 177
     assert set(geo.geom_type.to_pylist()) == {6}
     assert geo.is_empty().to_pylist().count(True) == 0
-    m = [0.8, -0.6, 0.6, 0.8, 10.0, -5.0]  # shapely order [a, b, d, e, xoff, yoff]
+    m = [0.8, -0.6, 10.0, 0.6, 0.8, -5.0]  # geo's AffineTransform::from([a, b, xoff, d, e, yoff]), see test_affine_matrix_order_is_geos
     t = geo.affine_transform(m).device.to_host()
     src = gs.device.to_host()
     assert np.array_equal(t.xy[:, 0], 0.8 * src.xy[:, 0] + -0.6 * src.xy[:, 1] + 10.0)
@@ -156,6 +156,21 @@ def test_geoseries_accessor_surface(ctx):
     assert rel_close(lengths["geodesic"], lengths["haversine"], 1e-2) and lengths["geodesic"].min() > 1e4
     with pytest.raises(ValueError):
         geo.geodesic_length("nope")
+
+
+def test_affine_matrix_order_is_geos(ctx):
+    """The reference binding hands the Python list to geo untouched (py-geopolars/src/geo.rs:10-13:
+    `series.affine_transform(transform)` with `transform: [f64; 6]`, and geo's `From<[T; 6]>` is
+    `AffineTransform::new(a, b, xoff, d, e, yoff)`), so the third number is the x offset — not `d` as the
+    docstring at georust/geoseries.py:33 says.  Parity follows the executable path."""
+    from geopolars_b200 import geoseries as G
+
+    G.set_context(ctx)
+    coord_t = pa.list_(pa.float64(), 2)
+    pts = G.GeoSeries(pa.array([(1.0, 2.0), (-3.0, 0.5)], type=coord_t))
+    out = pts.geo.affine_transform([2.0, 3.0, 100.0, 5.0, 7.0, 1000.0]).device.to_host().xy
+    assert out.tolist() == [[2.0 * 1.0 + 3.0 * 2.0 + 100.0, 5.0 * 1.0 + 7.0 * 2.0 + 1000.0],
+                            [2.0 * -3.0 + 3.0 * 0.5 + 100.0, 5.0 * -3.0 + 7.0 * 0.5 + 1000.0]]
 
 
 def test_reference_join_shapes(ctx):

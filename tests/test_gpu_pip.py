@@ -155,3 +155,111 @@ def test_empty_polygon_next_to_polygon_with_hole(ctx, og, conv):
     want, wc = og.contains_join(conv(polys), pts, use_grid=False)
     first, cnt = PipIndex(ctx.upload(polys)).query(pts, with_count=True)
     assert np.array_equal(first, want) and np.array_equal(cnt, wc) and (want == 1).any() and (want == -1).any()
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-20, 0.0), (1e-3, 0.0), (1.0, 1e6), (1e19, 0.0), (1e-12, 7.0), (1e-25, 0.0), (1e25, 0.0)])
+def test_part_extents_from_tiny_to_huge(ctx, og, conv, scale, offset):
+    """FP32 filter scale guard: parts whose extent is far below / above the float range of R^2 must not
+    be decided by the float filter; nybb-like parts (small extent at a 1e6 offset) must survive the float origin.
+    Points: random, every vertex, edge midpoints, and the neighbours of both one ulp away."""
+    from geopolars_b200.engine import PipIndex
+
+    xy, ro, go = synth.star_polygons(100, 10)
+    xy = xy * scale + offset
+    polys = GeoArrowArray.polygons(xy, ro, go)
+    pts = synth.uniform_points(20_000, scale=100.0) * scale + offset
+    mid = 0.5 * (xy[:-1] + xy[1:])
+    spec = np.concatenate([xy, mid])
+    pts = np.concatenate([pts, spec, np.nextafter(spec, np.inf), np.nextafter(spec, -np.inf)])
+    want_first, want_cnt = og.contains_join(conv(polys), pts, use_grid=False, threads=0)
+    idx = PipIndex(ctx.upload(polys))
+    first, cnt = idx.query(pts, with_count=True)
+    assert np.array_equal(first, want_first) and np.array_equal(cnt, want_cnt)
+    assert 0 < (want_first >= 0).sum() < len(pts)
+    st = idx.stats()
+    if scale in (1e-20, 1e-25, 1e19, 1e25):
+        assert st["parts_not_fast"] == 100  # outside 2^-50 <= R <= 2^50: no FP32 lists, the f64 walk decides
+    else:
+        assert st["parts_not_fast"] == 0
+
+
+def test_raster_cell_boundaries_and_census(ctx, og, conv):
+    """the 2-bit raster: points ON the fine-cell lattice (and one ulp either side), its census on the config-2 shapes,
+    and the deferred counter (exact re-evaluations) being small but non-zero on random points"""
+    from geopolars_b200.engine import PipIndex
+
+    xy, ro, go = synth.star_polygons(400, 20)
+    polys = GeoArrowArray.polygons(xy, ro, go)
+    idx = PipIndex(ctx.upload(polys))
+    st = idx.stats()
+    fg = st["fine_cells_per_axis"]
+    assert fg == st["coarse_cells_per_axis"] << st["raster_log2"] and st["raster_log2"] >= 4
+    total = fg * fg
+    walk, inside = st["raster_walk_cells"], st["raster_inside_cells"]
+    assert 0.03 < walk / total < 0.35, (walk, total)      # ring cells: the edge walk is the exception
+    assert 0.15 < inside / total < 0.60, (inside, total)  # ~37 % of the plane is inside a star
+    # lattice of fine-cell corners over a part of the grid, +- 1 ulp
+    x0, y0 = xy[:, 0].min(), xy[:, 1].min()
+    w, h = xy[:, 0].max() - x0, xy[:, 1].max() - y0
+    k = np.arange(0, fg + 1, 7, dtype=np.float64)
+    gx, gy = np.meshgrid(x0 + k / fg * w, y0 + (k[:200] + 3) / fg * h)
+    lat = np.stack([gx.ravel(), gy.ravel()], 1)
+    pts = np.concatenate([lat, np.nextafter(lat, np.inf), np.nextafter(lat, -np.inf), synth.uniform_points(400_000, scale=200.0)])
+    want_first, want_cnt = og.contains_join(conv(polys), pts, use_grid=True, threads=0)
+    first, cnt = idx.query(pts, with_count=True)
+    assert np.array_equal(first, want_first) and np.array_equal(cnt, want_cnt)
+    d = idx.stats()["deferred"]
+    assert 0 < d < 0.01 * len(pts), d
+
+
+def test_nested_and_covering_polygons(ctx, og, conv):
+    """raster codes compose: a cell inside two candidates, inside a third-or-later candidate, or inside one polygon and
+    on the ring of another must all take the walk; one giant polygon over many small ones exercises long candidate lists"""
+    from geopolars_b200.engine import PipIndex
+
+    sq = lambda x, y, s: [(x, y), (x + s, y), (x + s, y + s), (x, y + s), (x, y)]
+    shapes = [[sq(0, 0, 100)], [sq(10, 10, 50)], [sq(20, 20, 20)], [sq(25, 25, 5)], [sq(70, 70, 10), sq(72, 72, 3)]]
+    xy, ro, go = synth.star_polygons(64, 8, cell=12.5)
+    stars = GeoArrowArray.polygons(xy, ro, go)
+    for i in range(64):
+        shapes.append([xy[ro[i]:ro[i + 1]].tolist()])
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, shapes)
+    g = np.linspace(-2, 102, 209)
+    lat = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    pts = np.concatenate([lat, synth.uniform_points(300_000, scale=104.0) - 2.0])
+    want_first, want_cnt = og.contains_join(conv(polys), pts, use_grid=False, threads=0)
+    idx = PipIndex(ctx.upload(polys))
+    first, cnt = idx.query(pts, with_count=True)
+    assert np.array_equal(first, want_first) and np.array_equal(cnt, want_cnt)
+    assert want_cnt.max() >= 4
+    only_first = idx.query(pts)
+    assert np.array_equal(only_first, want_first)
+    lhs, rhs = idx.pairs(pts[:50_000])
+    assert len(lhs) == int(want_cnt[:50_000].sum())
+    # the same shapes as MULTIPOLYGON rows (parts of one row counted once)
+    multi = GeoArrowArray.from_shapes(GeometryType.MULTIPOLYGON, [[s] for s in shapes[:5]] + [[shapes[5 + i], shapes[6 + i]] for i in range(0, 62, 2)])
+    wf, wc = og.contains_join(conv(multi), pts, use_grid=False, threads=0)
+    f2, c2 = PipIndex(ctx.upload(multi)).query(pts, with_count=True)
+    assert np.array_equal(f2, wf) and np.array_equal(c2, wc)
+
+
+def test_unaligned_point_and_id_columns(ctx, og, conv):
+    """device columns that are only 16- / 4-byte aligned (slices) take the scalar load/store path of the streaming kernel"""
+    import torch
+
+    from geopolars_b200.engine import PipIndex
+
+    xy, ro, go = synth.star_polygons(100, 10)
+    polys = GeoArrowArray.polygons(xy, ro, go)
+    n = 100_003
+    pts = synth.uniform_points(n + 1, scale=100.0)
+    want, _ = og.contains_join(conv(polys), pts[1:], use_grid=True, threads=0)
+    idx = PipIndex(ctx.upload(polys))
+    d_pts = torch.from_numpy(pts).cuda()
+    d_ids = torch.full((n + 3,), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    idx.query_device(d_pts.data_ptr() + 16, n, d_ids.data_ptr() + 4)  # points from row 1, ids from element 1
+    ctx.synchronize()
+    got = d_ids.cpu().numpy()
+    assert got[0] == -7 and got[n + 1] == -7 and got[n + 2] == -7
+    assert np.array_equal(got[1:n + 1], want)
