@@ -134,11 +134,13 @@ SIGNATURES = {
     "gpl_y": (_INT, [_P, _P, _P, _INT]),
     "gpl_exterior": (_INT, [_P, _P, C.POINTER(_P)]),
     "gpl_explode": (_INT, [_P, _P, C.POINTER(_P)]),
+    "gpl_envelope_query": (_INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, _INT, _P, _INT]),
     "gpl_pip_index_build": (_INT, [_P, _P, C.POINTER(_P)]),
     "gpl_pip_index_free": (None, [_P]),
     "gpl_pip_index_bytes": (_I64, [_P]),
     "gpl_pip_index_stats": (_INT, [_P, _P, _P]),
     "gpl_contains_join": (_INT, [_P, _P, _P, _I64, _P, _P, _INT]),
+    "gpl_contains_join_counts": (_INT, [_P, _P, _P, _I64, _P, _P, _INT]),
     "gpl_contains_join_array": (_INT, [_P, _P, _P, _P, _P, _INT]),
     "gpl_contains_join_pairs": (_INT, [_P, _P, _P, _I64, _P, _P, C.POINTER(_I64), _INT]),
     "gpl_contains_join_host": (_INT, [_P, _P, _P, _I64, _P, _I64]),

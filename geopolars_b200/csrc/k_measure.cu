@@ -444,9 +444,43 @@ __global__ void k_envelope_polys(const double *__restrict__ b4, const uint8_t *_
     (void)vb;
 }
 
+// rstar's AABB tests on the per-row envelopes: mode 0 = `contains_envelope` (row envelope inside the closed query
+// box: RTree::locate_in_envelope, the reference's tests at spatial_index.rs:361-430), mode 1 = `intersects` (closed
+// intervals: locate_in_envelope_intersecting / the candidate test of intersection_candidates_with_other_tree, :74-76)
+__global__ void k_envelope_query(const double *__restrict__ b4, const uint8_t *__restrict__ has, int64_t n, double qx0, double qy0,
+                                 double qx1, double qy1, int mode, uint8_t *__restrict__ out_bytes) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x0 = b4[4 * i], y0 = b4[4 * i + 1], x1 = b4[4 * i + 2], y1 = b4[4 * i + 3];
+    bool m;
+    if (mode == 0) m = x0 >= qx0 && y0 >= qy0 && x1 <= qx1 && y1 <= qy1;
+    else m = x0 <= qx1 && x1 >= qx0 && y0 <= qy1 && y1 >= qy0;
+    out_bytes[i] = (m && has[i]) ? 1 : 0;  // NaN bounds (empty row) fail every comparison anyway
+}
+
 }  // namespace gpl
 
 using namespace gpl;
+
+extern "C" int gpl_envelope_query(gpl_ctx *ctx, const gpl_array *in, double minx, double miny, double maxx, double maxy, int mode,
+                                  uint8_t *out_bitmap, int mem) {
+    GPL_REQUIRE(ctx && in && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_envelope_query: NULL argument");
+    GPL_REQUIRE(mode == 0 || mode == 1, GPL_ERR_INVALID_ARG, "gpl_envelope_query: mode must be 0 (contained) or 1 (intersecting)");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = in->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<double> b4;
+    Scratch<uint8_t> vb, hit, bm;
+    GPL_TRY(b4.get(ctx, (size_t)n * 4));
+    GPL_TRY(vb.get(ctx, (size_t)n));
+    GPL_TRY(hit.get(ctx, (size_t)n));
+    GPL_TRY(envelope_raw(ctx, in, b4.p, vb.p));
+    GPL_LAUNCH(ctx, k_envelope_query, (int)ceil_div(n, 256), 256, 0, b4.p, vb.p, n, minx, miny, maxx, maxy, mode, hit.p);
+    if (mem == GPL_DEVICE) return pack_bits(ctx, hit.p, out_bitmap, n);
+    GPL_TRY(bm.get(ctx, (size_t)(n + 7) / 8));
+    GPL_TRY(pack_bits(ctx, hit.p, bm.p, n));
+    return deliver(ctx, out_bitmap, bm.p, (size_t)(n + 7) / 8, GPL_HOST);
+}
 
 extern "C" int gpl_area(gpl_ctx *ctx, const gpl_array *in, double *out, int mem) {
     GPL_REQUIRE(ctx && in && out, GPL_ERR_INVALID_ARG, "gpl_area: NULL argument");

@@ -1422,15 +1422,22 @@ struct __align__(16) StreamSmem {
 __device__ __forceinline__ void ld256s(const double2 *p, double2 &a, double2 &b) {  // read-once stream: evict first
     asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
-template <bool LEAN>
+// HIST: per-polygon hit counts (config 4's all-reduce input) in the same pass: 32-bit bins privatised per CTA in shared
+// memory behind the queues, flushed with one 64-bit global atomic per non-zero bin when the CTA retires.
+template <bool LEAN, bool HIST>
 __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
                                                                                   const uint8_t *__restrict__ pts_validity, int64_t n_pts,
                                                                                   int32_t *__restrict__ first_id, int32_t *__restrict__ count,
                                                                                   unsigned long long *__restrict__ n_deferred,
                                                                                   uint32_t *__restrict__ deferred_list, uint32_t list_cap,
-                                                                                  int vec_ok) {
+                                                                                  int vec_ok, unsigned long long *__restrict__ hist, int32_t n_bins) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+    unsigned int *bins = reinterpret_cast<unsigned int *>(smem_raw + sizeof(StreamSmem));
+    if (HIST) {
+        for (int32_t b = threadIdx.x; b < n_bins; b += kQueryThreads) bins[b] = 0u;
+        __syncthreads();
+    }
     const GridParams &g = ix.grid;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double2 *q_pts = sm.q_pts[wid];
@@ -1457,6 +1464,7 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
             }
             first_id[idx] = first;
             if (want_count) count[idx] = cnt;
+            if (HIST && first >= 0 && first < n_bins) atomicAdd(&bins[first], 1u);
         }
     };
 
@@ -1506,6 +1514,7 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
             if (code[k] == 1u || code[k] == 2u) {
                 const int2 cand = __ldg(ix.cand01 + (int64_t)(fy[k] >> g.rs) * g.gx + (fx[k] >> g.rs));
                 id[k] = code[k] == 1u ? cand.x : cand.y;
+                if (HIST && id[k] >= 0 && id[k] < n_bins) atomicAdd(&bins[id[k]], 1u);
             }
         }
         // stage 3: ids out (the queued ones are overwritten by the walk)
@@ -1545,6 +1554,13 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
         }
     }
     if (qn > 0) walk_queued(lane, lane < qn);
+    if (HIST) {
+        __syncthreads();
+        for (int32_t b = threadIdx.x; b < n_bins; b += kQueryThreads) {
+            const unsigned int v = bins[b];
+            if (v) atomicAdd(hist + b, (unsigned long long)v);
+        }
+    }
 }
 
 // Exact re-evaluation of the points the walk marked kDeferred (those whose filters could not
@@ -1553,7 +1569,8 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
 // counter is zero.  One thread per deferred point, taken from the list the query kernel appended to; if
 // the list overflowed, the id column is scanned for the marker instead.
 __device__ __forceinline__ void deferred_point(const IndexView &ix, const double2 *__restrict__ pts, int64_t i,
-                                               int32_t *__restrict__ first_id, int32_t *__restrict__ count) {
+                                               int32_t *__restrict__ first_id, int32_t *__restrict__ count,
+                                               unsigned long long *__restrict__ hist) {
     const double2 p = pts[i];
     const CellRec cell = ix.cells[coarse_cell(ix.grid, p.x, p.y)];
     int32_t first = -1, cnt = 0, last_geom = -1;
@@ -1571,21 +1588,23 @@ __device__ __forceinline__ void deferred_point(const IndexView &ix, const double
     }
     first_id[i] = first;
     if (count) count[i] = cnt;
+    if (hist && first >= 0) atomicAdd(hist + first, 1ULL);  // the streaming kernel counted decided points only
 }
 __global__ void __launch_bounds__(256) k_pip_deferred(const IndexView ix, const double2 *__restrict__ pts, int64_t n_pts,
                                                       int32_t *__restrict__ first_id, int32_t *__restrict__ count,
                                                       unsigned long long *__restrict__ n_deferred,
                                                       const uint32_t *__restrict__ deferred_list, uint32_t list_cap,
-                                                      unsigned long long *__restrict__ n_deferred_total) {
+                                                      unsigned long long *__restrict__ n_deferred_total,
+                                                      unsigned long long *__restrict__ hist) {
     const unsigned long long nd = *n_deferred;
     if (nd == 0ULL) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if (nd <= list_cap) {
         for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)nd; k += stride)
-            deferred_point(ix, pts, (int64_t)deferred_list[k], first_id, count);
+            deferred_point(ix, pts, (int64_t)deferred_list[k], first_id, count, hist);
     } else {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride)
-            if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count);
+            if (first_id[i] == kDeferred) deferred_point(ix, pts, i, first_id, count, hist);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_deferred_total) atomicAdd(n_deferred_total, nd);
 }
@@ -1649,23 +1668,36 @@ static int query_grid(int64_t n, bool lean = false) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
 // streaming kernel: exactly the resident CTAs (persistent warps, one tile of 128 points per warp and iteration)
-template <bool LEAN>
-static int stream_grid(int64_t n) {
-    static const int per_sm = [] {
-        int occ = 0;
-        cudaFuncSetAttribute(k_pip_stream<LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN>, kQueryThreads, sizeof(StreamSmem)) != cudaSuccess || occ < 1) occ = 1;
-        (void)cudaGetLastError();
-        const int cap = env_int("GPL_PIP_STREAM_CTAS_PER_SM", 0);
-        return cap > 0 ? std::min(cap, occ) : occ;
-    }();
+constexpr int32_t kHistFuseMaxBins = 12288;  // 48 KB of bins per CTA: three CTAs per SM still fit next to the queues
+template <bool LEAN, bool HIST>
+static int stream_grid(int64_t n, size_t smem_bytes) {
+    static size_t attr_bytes = 0;
+    if (smem_bytes > attr_bytes) {
+        cudaFuncSetAttribute(k_pip_stream<LEAN, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        attr_bytes = smem_bytes;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN, HIST>, kQueryThreads, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    (void)cudaGetLastError();
+    static const int cap = env_int("GPL_PIP_STREAM_CTAS_PER_SM", 0);
+    const int per_sm = cap > 0 ? std::min(cap, occ) : occ;
     const int64_t want = ceil_div(ceil_div(n, kTilePts), kStreamWarps);
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
+template <bool LEAN, bool HIST>
+static void launch_stream(const IndexView &v, const double2 *pts, const uint8_t *val, int64_t m, int32_t *first, int32_t *cnt,
+                          const gpl_pip_index *idx, int vec_ok, unsigned long long *hist, int32_t n_bins, cudaStream_t stream) {
+    const size_t smem = sizeof(StreamSmem) + (HIST ? sizeof(unsigned int) * (size_t)n_bins : 0);
+    k_pip_stream<LEAN, HIST><<<stream_grid<LEAN, HIST>(m, smem), kQueryThreads, smem, stream>>>(v, pts, val, m, first, cnt, idx->n_deferred,
+                                                                                             idx->deferred_list, idx->deferred_cap, vec_ok, hist,
+                                                                                             n_bins);
+}
 
+// hist (optional, device, n_geoms u64): += number of points whose first containing row is that polygon
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
-              int32_t *first_dev, int32_t *count_dev, cudaStream_t stream) {
+              int32_t *first_dev, int32_t *count_dev, cudaStream_t stream, unsigned long long *hist = nullptr) {
     if (n == 0) return GPL_OK;
+    const bool fuse_hist = hist != nullptr && idx->n_geoms <= kHistFuseMaxBins;
     const double2 *pts = reinterpret_cast<const double2 *>(pts_dev);
     const IndexView v = view_of(idx);
     static const bool legacy = env_int("GPL_PIP_LEGACY", 0) != 0;  // round-1 kernel: every point walks (A/B measurements)
@@ -1700,16 +1732,28 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
                                 (cnt == nullptr || (reinterpret_cast<uintptr_t>(cnt) & 7) == 0))
                                    ? 1
                                    : 0;
-            if (idx->lean_ok)
-                k_pip_stream<true><<<stream_grid<true>(m), kQueryThreads, sizeof(StreamSmem), stream>>>(
-                    v, pts + lo, val, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok);
-            else
-                k_pip_stream<false><<<stream_grid<false>(m), kQueryThreads, sizeof(StreamSmem), stream>>>(
-                    v, pts + lo, val, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok);
+            const int32_t nb = (int32_t)idx->n_geoms;
+            if (idx->lean_ok) {
+                if (fuse_hist) launch_stream<true, true>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, hist, nb, stream);
+                else launch_stream<true, false>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, nullptr, 0, stream);
+            } else {
+                if (fuse_hist) launch_stream<false, true>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, hist, nb, stream);
+                else launch_stream<false, false>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, nullptr, 0, stream);
+            }
         }
+        const bool fused_here = fuse_hist && !legacy;
         k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap,
-                                                     idx->n_deferred + 1);
+                                                     idx->n_deferred + 1, fused_here ? hist : nullptr);
         ctx->launches += 2;
+        if (hist && !fused_here) {  // many polygons (or the legacy kernel): count from the id column
+            const bool use_smem = idx->n_geoms <= kHistSmemBins;
+            const size_t dyn = use_smem ? sizeof(unsigned int) * (size_t)idx->n_geoms : 0;
+            if (dyn > 48 * 1024) GPL_CUDA(cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            const int per_sm = use_smem ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(dyn, 1))) : 4;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(m, 2048), (int64_t)kSMs * per_sm));
+            k_histogram<<<grid, 512, dyn, stream>>>(first_dev + lo, m, hist, idx->n_geoms, use_smem ? 1 : 0);
+            ctx->launches++;
+        }
     }
     GPL_CUDA(cudaGetLastError());
     return GPL_OK;
@@ -2016,6 +2060,30 @@ extern "C" int gpl_contains_join(gpl_ctx *ctx, const gpl_pip_index *idx, const d
     GPL_TRY(pip_query(ctx, idx, pts.p, nullptr, n_points, ids.p, count ? cnt.p : nullptr, ctx->stream));
     GPL_CUDA(cudaMemcpyAsync(first_id, ids.p, sizeof(int32_t) * n_points, cudaMemcpyDeviceToHost, ctx->stream));
     if (count) GPL_CUDA(cudaMemcpyAsync(count, cnt.p, sizeof(int32_t) * n_points, cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPL_OK;
+}
+
+extern "C" int gpl_contains_join_counts(gpl_ctx *ctx, const gpl_pip_index *idx, const double *points_xy, int64_t n_points,
+                                        int32_t *first_id, uint64_t *counts, int mem) {
+    GPL_REQUIRE(ctx && idx && first_id && counts && (points_xy || n_points == 0), GPL_ERR_INVALID_ARG,
+                "gpl_contains_join_counts: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    if (n_points == 0) return GPL_OK;
+    if (mem == GPL_DEVICE)
+        return pip_query(ctx, idx, points_xy, nullptr, n_points, first_id, nullptr, ctx->stream, reinterpret_cast<unsigned long long *>(counts));
+    Scratch<double> pts;
+    Scratch<int32_t> ids;
+    Scratch<unsigned long long> cnt;
+    const size_t ng = (size_t)idx->n_geoms;
+    GPL_TRY(pts.get(ctx, (size_t)n_points * 2));
+    GPL_TRY(ids.get(ctx, (size_t)n_points));
+    GPL_TRY(cnt.get(ctx, ng));
+    GPL_CUDA(cudaMemcpyAsync(pts.p, points_xy, sizeof(double) * 2 * n_points, cudaMemcpyHostToDevice, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(cnt.p, counts, sizeof(uint64_t) * ng, cudaMemcpyHostToDevice, ctx->stream));
+    GPL_TRY(pip_query(ctx, idx, pts.p, nullptr, n_points, ids.p, nullptr, ctx->stream, cnt.p));
+    GPL_CUDA(cudaMemcpyAsync(first_id, ids.p, sizeof(int32_t) * n_points, cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(counts, cnt.p, sizeof(uint64_t) * ng, cudaMemcpyDeviceToHost, ctx->stream));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
 }

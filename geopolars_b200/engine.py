@@ -351,6 +351,16 @@ def bounds(a: DeviceArray) -> np.ndarray:
     return out
 
 
+def envelope_query(a: DeviceArray, box, intersecting: bool = False) -> np.ndarray:
+    """SpatialIndex.r_tree.locate_in_envelope(&AABB::from_corners(..)) (spatial_index.rs:385-387): rows whose envelope
+    lies inside the closed box; `intersecting=True`: rows whose envelope meets it (the join's candidate test)."""
+    n = len(a)
+    bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+    x0, y0, x1, y1 = (float(v) for v in box)
+    check(a.ctx.lib.gpl_envelope_query(a.ctx._h, a._h, x0, y0, x1, y1, 1 if intersecting else 0, _np_ptr(bm), GPL_HOST))
+    return _bits(bm, n)
+
+
 def convex_hull(a: DeviceArray) -> DeviceArray:
     return _out_array(a.ctx, a.ctx.lib.gpl_convex_hull, a._h)
 
@@ -474,6 +484,20 @@ class PipIndex:
         """all buffers already in HBM (bench `value` path): one kernel launch, stream ordered."""
         check(self.ctx.lib.gpl_contains_join(self.ctx._h, self._h, C.c_void_p(points_ptr), n, C.c_void_p(first_ptr),
                                              C.c_void_p(count_ptr) if count_ptr else None, GPL_DEVICE))
+
+    def query_device_counts(self, points_ptr: int, n: int, first_ptr: int, counts_ptr: int) -> None:
+        """join + per-polygon hit counts (u64 column, accumulated) in one pass; all buffers in HBM"""
+        check(self.ctx.lib.gpl_contains_join_counts(self.ctx._h, self._h, C.c_void_p(points_ptr), n, C.c_void_p(first_ptr),
+                                                    C.c_void_p(counts_ptr), GPL_DEVICE))
+
+    def query_counts(self, points_xy: np.ndarray):
+        """(first_id, per-polygon hit counts) from host points"""
+        pts = np.ascontiguousarray(points_xy, dtype=np.float64).reshape(-1, 2)
+        n = pts.shape[0]
+        first = np.empty(n, dtype=np.int32)
+        counts = np.zeros(len(self.polygons), dtype=np.uint64)
+        check(self.ctx.lib.gpl_contains_join_counts(self.ctx._h, self._h, _np_ptr(pts), n, _np_ptr(first), _np_ptr(counts), GPL_HOST))
+        return first, counts
 
     def query_array(self, points: DeviceArray, with_count: bool = False):
         n = len(points)

@@ -224,6 +224,13 @@ int gpl_y(gpl_ctx *ctx, const gpl_array *in, double *out, int mem);
 int gpl_exterior(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
 int gpl_explode(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
 
+/* SpatialIndex envelope queries (spatial_index.rs:206-312 builds one AABB per row, the tests at :361-430 query them
+ * with rstar's RTree::locate_in_envelope): out bit i = row i's envelope lies inside the closed box [min,max]
+ * (mode 0, `AABB::contains_envelope`) or intersects it (mode 1, closed intervals — the candidate test of the join,
+ * :74-76).  Rows without an envelope (null / empty) never match (the reference unwraps and panics on them). */
+int gpl_envelope_query(gpl_ctx *ctx, const gpl_array *in, double minx, double miny, double maxx, double maxy, int mode,
+                       uint8_t *out_bitmap, int mem);
+
 /* ---------------------------------------------------------------- spatial join ----------- */
 /* Replaces SpatialIndex (spatial_index.rs:314-350) for the polygon side of a points-in-polygons
  * join: per-polygon bounding boxes in a uniform grid (candidate generation, closed intervals like
@@ -242,6 +249,10 @@ int gpl_pip_index_stats(gpl_ctx *ctx, const gpl_pip_index *idx, int64_t *out8);
  * containing rows.  points: xy interleaved, n points, in `mem`. */
 int gpl_contains_join(gpl_ctx *ctx, const gpl_pip_index *idx, const double *points_xy, int64_t n_points,
                       int32_t *first_id, int32_t *count, int mem);
+/* the join and the per-polygon hit counts of config 4 in ONE pass over the points: counts[n polygon rows] (u64) +=
+ * number of points whose first containing row is that polygon (what gpl_join_histogram computes from first_id). */
+int gpl_contains_join_counts(gpl_ctx *ctx, const gpl_pip_index *idx, const double *points_xy, int64_t n_points,
+                             int32_t *first_id, uint64_t *counts, int mem);
 /* same with the points given as a POINT gpl_array (null points -> -1) */
 int gpl_contains_join_array(gpl_ctx *ctx, const gpl_pip_index *idx, const gpl_array *points, int32_t *first_id,
                             int32_t *count, int mem);

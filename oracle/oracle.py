@@ -33,12 +33,59 @@ class _OgArray(C.Structure):
     ]
 
 
+def _cpu_signature():
+    """identifies the host CPU (model + ISA flags): a -march=native build is only valid where it was made"""
+    import hashlib
+
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name") and not model:
+                    model = ln.split(":", 1)[1].strip()
+                elif ln.startswith("flags") and not flags:
+                    flags = ln.split(":", 1)[1].strip()
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    return model, hashlib.sha1((model + "|" + flags).encode()).hexdigest()[:12]
+
+
+_build_info = {"flags": None, "cpu": None, "so": None, "native": False}
+
+
 def build(force: bool = False) -> str:
-    """Compile the oracle with the recipe in oracle/Makefile (building the checker is not using it)."""
+    """Compile the oracle with the recipe in oracle/Makefile (building the checker is not using it).
+    Returns the library to load: the -march=native build for THIS host when it can be made (BASELINE.md's
+    `-O3 -march=native -ffp-contract=off` CPU arm), else the portable build that ships with the snapshot."""
     src = os.path.join(_HERE, "geo_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
-    return _SO
+    model, sig = _cpu_signature()
+    _build_info.update(cpu=model, so=_SO, native=False)
+    try:
+        _build_info["flags"] = subprocess.check_output(["make", "-C", _HERE, "-s", "flags"], text=True).strip()
+    except Exception:
+        _build_info["flags"] = "portable build (flags unknown)"
+    if os.environ.get("GEO_ORACLE_NATIVE", "1") != "0":
+        ndir = os.path.join(_HERE, "_native", sig)
+        nso = os.path.join(ndir, "libgeo_oracle.so")
+        try:
+            if force or not os.path.exists(nso) or os.path.getmtime(nso) < os.path.getmtime(src):
+                subprocess.check_call(["make", "-C", _HERE, "-s", "native", f"NATIVE_DIR={os.path.join('_native', sig)}"],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(os.path.join(ndir, "flags.txt")) as f:
+                _build_info.update(flags=f.read().strip(), so=nso, native=True)
+        except Exception:
+            pass  # no compiler on this host: the portable build stands
+    return _build_info["so"]
+
+
+def build_info() -> dict:
+    """compiler flags, CPU model and path of the library in use (bench.py prints them next to the CPU arm)"""
+    lib()
+    return dict(_build_info)
 
 
 _lib = None
@@ -47,8 +94,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(_SO)
+        so = build()
+        try:
+            L = C.CDLL(so)
+        except OSError:
+            L = C.CDLL(_SO)
+            _build_info.update(so=_SO, native=False)
         L.og_orient2d.restype = C.c_double
         L.og_orient2d.argtypes = [C.c_double] * 6
         L.og_orient2d_adapt_calls.restype = C.c_int64
@@ -157,6 +208,22 @@ def envelope(arr: OGArray, threads: int = 1):
     valid = np.empty(len(arr), dtype=np.uint8)
     lib().og_envelope(C.byref(s), _p(out), _p(valid), C.c_int(threads))
     return out, valid.astype(bool)
+
+
+def envelope_query(arr: OGArray, box, mode: int = 0) -> np.ndarray:
+    """rstar 0.11 `RTree::locate_in_envelope(&AABB::from_corners(lo, hi))` over the per-row envelopes
+    (geopolars/src/spatial_index.rs:206-312 builds them, the tests at :361-430 query them): mode 0 = rows whose
+    envelope lies INSIDE the closed box (`AABB::contains_envelope`: lower <= lower' and upper' <= upper per axis);
+    mode 1 = rows whose envelope INTERSECTS it (`locate_in_envelope_intersecting`, the candidate test of the join,
+    :74-76).  Rows without an envelope (empty / null) never match."""
+    b, has = envelope(arr)
+    x0, y0, x1, y1 = (float(v) for v in box)
+    has = has & ~np.isnan(b).any(axis=1)
+    if mode == 0:
+        m = (b[:, 0] >= x0) & (b[:, 1] >= y0) & (b[:, 2] <= x1) & (b[:, 3] <= y1)
+    else:
+        m = (b[:, 0] <= x1) & (b[:, 2] >= x0) & (b[:, 1] <= y1) & (b[:, 3] >= y0)
+    return m & has
 
 
 def euclidean_length(arr: OGArray, threads: int = 1) -> np.ndarray:

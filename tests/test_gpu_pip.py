@@ -263,3 +263,50 @@ def test_unaligned_point_and_id_columns(ctx, og, conv):
     got = d_ids.cpu().numpy()
     assert got[0] == -7 and got[n + 1] == -7 and got[n + 2] == -7
     assert np.array_equal(got[1:n + 1], want)
+
+
+def test_reference_golden_envelope_queries_gpu(ctx, og, conv):
+    """spatial_index.rs:361-430 on the device: points -> rows {0,1,2,8}; the two squares -> row {0}; candidates -> {0,1}"""
+    from geopolars_b200 import engine as E
+    from test_oracle_cpu import AABB_POINTS, AABB_POLYS, AABB_QUERY
+
+    pts = GeoArrowArray.from_shapes(GeometryType.POINT, AABB_POINTS)
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, AABB_POLYS)
+    d_pts, d_polys = ctx.upload(pts), ctx.upload(polys)
+    assert np.nonzero(E.envelope_query(d_pts, AABB_QUERY))[0].tolist() == [0, 1, 2, 8]
+    assert np.nonzero(E.envelope_query(d_polys, AABB_QUERY))[0].tolist() == [0]
+    assert np.nonzero(E.envelope_query(d_polys, AABB_QUERY, intersecting=True))[0].tolist() == [0, 1]
+    # the grid candidate stage of the join agrees with the AABB intersection test: every point whose degenerate box meets a
+    # polygon's envelope reaches the exact test (here: candidates of square 0 are the points inside its closed envelope)
+    idx = E.PipIndex(d_polys)
+    first, cnt = idx.query(np.asarray(AABB_POINTS), with_count=True)
+    assert first.tolist() == [-1, 0, -1, -1, -1, 1, -1, -1, -1]  # (1,1) inside square 0, (-1,-1) inside square 1; edges excluded
+    # random columns against the oracle, both modes, incl. null and empty rows
+    xy, ro, go = synth.star_polygons(400, 20)
+    stars = GeoArrowArray.polygons(xy, ro, go)
+    d = ctx.upload(stars)
+    for box in [(0.0, 0.0, 200.0, 200.0), (33.0, 41.5, 120.25, 77.0), (1e3, 1e3, 2e3, 2e3)]:
+        for mode in (0, 1):
+            assert np.array_equal(E.envelope_query(d, box, intersecting=bool(mode)), og.envelope_query(conv(stars), box, mode))
+    mixed = GeoArrowArray.from_shapes(GeometryType.MULTIPOLYGON, _holes_and_multis())
+    for mode in (0, 1):
+        assert np.array_equal(E.envelope_query(ctx.upload(mixed), (-1.0, -1.0, 16.0, 16.0), intersecting=bool(mode)),
+                              og.envelope_query(conv(mixed), (-1.0, -1.0, 16.0, 16.0), mode))
+
+
+def test_join_counts_fused_histogram(ctx, og, conv):
+    """gpl_contains_join_counts: ids + per-polygon hit counts in one pass (bins in shared memory up to 12288 polygon rows,
+    the id-column histogram beyond); boundary points (deferred to the exact kernel) must be counted exactly once"""
+    from geopolars_b200.engine import PipIndex
+
+    for m, grid in ((400, 20), (16_900, 130)):
+        xy, ro, go = synth.star_polygons(m, grid)
+        polys = GeoArrowArray.polygons(xy, ro, go)
+        pts = np.concatenate([synth.uniform_points(300_000, scale=grid * 10.0), xy[:2000], 0.5 * (xy[:2000] + xy[1:2001])])
+        want, _ = og.contains_join(conv(polys), pts, use_grid=True, threads=0)
+        idx = PipIndex(ctx.upload(polys))
+        first, counts = idx.query_counts(pts)
+        assert np.array_equal(first, want)
+        assert np.array_equal(counts.astype(np.int64), np.bincount(want[want >= 0], minlength=m))
+        f2, c2 = idx.query_counts(pts)  # counts accumulate per call from a zeroed column: same result again
+        assert np.array_equal(f2, want) and np.array_equal(c2, counts)

@@ -35,6 +35,30 @@ def test_reference_golden_contains_vector(og, conv):
     assert np.array_equal(first, first2)
 
 
+# The reference's two SpatialIndex tests (geopolars/src/spatial_index.rs:361-430), restated literally.
+AABB_POINTS = [(0.0, 10.0), (1.0, 1.0), (10.0, 0.0), (1.0, -1.0), (0.0, -10.0), (-1.0, -1.0), (-10.0, 0.0), (-1.0, 1.0), (0.0, 10.0)]
+AABB_POLYS = [[[(0.0, 0.0), (10.0, 0.0), (10.0, 10.0), (0.0, 10.0), (0.0, 0.0)]],
+              [[(0.0, 0.0), (-10.0, 0.0), (-10.0, -10.0), (0.0, -10.0), (0.0, 0.0)]]]
+AABB_QUERY = (0.0, 0.0, 20.0, 20.0)
+
+
+def test_reference_golden_envelope_queries(og, conv):
+    """spatial_index_points (:361-393): `locate_in_envelope(AABB [0,0]-[20,20])` over 9 points returns exactly rows
+    {0, 1, 2, 8} (closed intervals: (10,0) and (0,10) lie on the box's edge and count).
+    spatial_index_polygons (:395-430): over the two squares it returns exactly row 0 — the second square touches the
+    query box at the corner (0,0) only and its envelope [-10,-10]-[0,0] is not INSIDE the box (rstar's
+    locate_in_envelope is containment, not intersection)."""
+    pts = GeoArrowArray.from_shapes(GeometryType.POINT, AABB_POINTS)
+    assert np.nonzero(og.envelope_query(conv(pts), AABB_QUERY))[0].tolist() == [0, 1, 2, 8]
+    polys = GeoArrowArray.from_shapes(GeometryType.POLYGON, AABB_POLYS)
+    assert np.nonzero(og.envelope_query(conv(polys), AABB_QUERY))[0].tolist() == [0]
+    # the join's candidate test is intersection with closed intervals (:74-76): the corner-touching square IS a candidate
+    assert np.nonzero(og.envelope_query(conv(polys), AABB_QUERY, mode=1))[0].tolist() == [0, 1]
+    # NodeEnvelope of a point is the degenerate box (:289); of a polygon its exterior's bounding_rect (:218-226)
+    b, v = og.envelope(conv(polys))
+    assert v.all() and b.tolist() == [[0.0, 0.0, 10.0, 10.0], [-10.0, -10.0, 0.0, 0.0]]
+
+
 def test_config1_cities_points(og, conv):
     """BASELINE config 1: centroid(points) == points bit-exactly, area == 0, 202 rows"""
     arr, _ = load("cities")
