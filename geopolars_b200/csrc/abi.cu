@@ -200,6 +200,11 @@ extern "C" void gpl_ctx_destroy(gpl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->trim();
     for (auto &kv : ctx->live) cudaFree(kv.first);
+    if (ctx->l2_limit_saved) {  // undo the L2 carve-out a join index asked for (k_pip.cu l2_pin)
+        (void)cudaCtxResetPersistingL2Cache();
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_prev_limit);
+        (void)cudaGetLastError();
+    }
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

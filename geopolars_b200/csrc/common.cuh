@@ -64,6 +64,8 @@ struct gpl_ctx {
     size_t bytes_reserved = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // device limits, read once at creation
     const void *l2_pinned = nullptr;               // slab currently covered by the access-policy window
+    size_t l2_prev_limit = 0, l2_cur_limit = 0;    // cudaLimitPersistingL2CacheSize before the first pin / now
+    bool l2_limit_saved = false;
 
     int alloc(size_t bytes, void **out);
     void release(void *p);

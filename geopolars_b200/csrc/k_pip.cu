@@ -145,8 +145,6 @@ struct gpl_pip_index {
     unsigned long long *n_deferred = nullptr;  // device counters inside the slab: [0] this launch, [1] since the build
     uint32_t *deferred_list = nullptr;         // indices of deferred points (grown on demand)
     uint32_t deferred_cap = 0;
-    size_t prev_l2_limit = 0;         // cudaLimitPersistingL2CacheSize before this index pinned its slab
-    bool l2_limit_saved = false;
     int64_t bytes = 0;
 };
 
@@ -1765,8 +1763,9 @@ using namespace gpl;
 
 // Keep the hot part of the index slab resident in the 126 MB L2 while 1.6 GB of points stream past it: mark it
 // as a persisting access-policy window on the context stream (the point loads are ld.global.cs,
-// i.e. evict-first).  Best effort: failures only cost performance.  The device-wide carve-out is restored and the
-// persisting lines are released when the index that set them is freed.
+// i.e. evict-first).  Best effort: failures only cost performance.  The device-wide carve-out only ever grows while
+// the context lives and is restored by gpl_ctx_destroy; the window is dropped and the persisting lines are released
+// when the index that set them is freed (neither call waits for running kernels: they are cache hints).
 static void l2_pin(gpl_pip_index *idx, bool on) {
     gpl_ctx *ctx = idx->ctx;
     static const bool enabled = env_int("GPL_L2_PIN", 1) != 0;
@@ -1776,12 +1775,19 @@ static void l2_pin(gpl_pip_index *idx, bool on) {
     if (on) {
         const size_t want = idx->hot_bytes ? idx->hot_bytes : idx->slab_bytes;
         size_t carve = std::min<size_t>(want, ctx->l2_persist_max);
-        size_t prev = 0;
-        if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
-            idx->prev_l2_limit = prev;
-            idx->l2_limit_saved = true;
+        if (!ctx->l2_limit_saved) {
+            size_t prev = 0;
+            if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
+                ctx->l2_prev_limit = prev;
+                ctx->l2_limit_saved = true;
+                ctx->l2_cur_limit = prev;
+            }
         }
-        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::max(carve, prev));
+        if (carve > ctx->l2_cur_limit) {
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            ctx->l2_cur_limit = carve;
+        }
+        carve = std::min(carve, ctx->l2_cur_limit);
         size_t win = std::min<size_t>(want, ctx->l2_window_max);
         attr.accessPolicyWindow.base_ptr = idx->slab;
         attr.accessPolicyWindow.num_bytes = win;
@@ -1797,12 +1803,7 @@ static void l2_pin(gpl_pip_index *idx, bool on) {
         ctx->l2_pinned = nullptr;
     }
     (void)cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-    if (!on) {
-        // queries of this index may still be running: the reset must not pull the lines from under them
-        (void)cudaStreamSynchronize(ctx->stream);
-        (void)cudaCtxResetPersistingL2Cache();
-        if (idx->l2_limit_saved) (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, idx->prev_l2_limit);
-    }
+    if (!on) (void)cudaCtxResetPersistingL2Cache();
     (void)cudaGetLastError();
 }
 
