@@ -7,8 +7,8 @@ points `.contains()`-joined against 10 000 64-vertex star polygons (SURVEY.md §
 the only exchange step this path has).
 
 One "step" = one pass of the hot path over one batch: [N>1: NCCL broadcast of the polygon coordinates] + polygon
-index build + the point-in-polygon kernel over all of the rank's points, which also accumulates the per-polygon hit
-counts [+ N>1: all-reduce of the counts].  `value` = points processed by all ranks / max-over-ranks device time,
+index build + the point-in-polygon kernel over all of the rank's points + the per-polygon hit counts [+ N>1: all-reduce
+of the counts].  `value` = points processed by all ranks / max-over-ranks device time,
 inputs resident in HBM.  `e2e` = the same join through the C ABI from pinned HOST buffers (H2D of the points and D2H
 of the ids inside the timed region, chunked and overlapped).
 
@@ -190,7 +190,7 @@ class JoinWorkload:
             self.baseline = "BASELINE configs[3]; SURVEY.md config 4 generator (1 B points at 8 GPUs)"
         self.unit_name = "points"
         self.scaling = "weak"
-        self.kernel = "k_pip_stream<LEAN,HIST> (+ k_pip_deferred)"
+        self.kernel = "k_pip_stream<LEAN> (+ k_pip_deferred)"
         self.traffic_file = "r2_pip_traffic.json"
 
     # --- inputs resident in HBM ---------------------------------------------------------------------------
@@ -248,10 +248,13 @@ class JoinWorkload:
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(e.stream)
-        self.idx.query_device_counts(self.pts.data_ptr(), self.n, self.ids.data_ptr(), counts.data_ptr())
+        self.idx.query_device(self.pts.data_ptr(), self.n, self.ids.data_ptr())
         if events is not None:
             e1.record(e.stream)
             events.append((e0, e1))
+        from geopolars_b200 import engine as E
+
+        E.check(e.ctx.lib.gpl_join_histogram(e.ctx._h, self.ids.data_ptr(), self.n, counts.data_ptr(), self.n_polys, E.GPL_DEVICE))
         if e.world > 1:
             dist.all_reduce(counts)
             if self.gather:
@@ -261,7 +264,7 @@ class JoinWorkload:
     def describe_step(self):
         e = self.env
         s = ("NCCL broadcast of polygon coords + " if e.world > 1 else "") + "polygon index build (2 cooperative launches) + " \
-            "point-in-polygon kernel over all points with fused per-polygon hit counts"
+            "point-in-polygon kernel over all points + per-polygon hit counts (histogram of the id column)"
         if e.world > 1:
             s += " + counts all-reduce" + (" + id column gathered to rank 0" if self.gather else "")
         return s

@@ -503,10 +503,10 @@ __global__ void __launch_bounds__(128) k_geodesic_length(int type, int64_t n_geo
         default: break;
         }
         s = warp_sum(s);
-        ok = __all_sync(0xffffffffu, ok) && bit_get(validity, g);  // a null row stays null (area / length / x / y do the same)
+        ok = __all_sync(0xffffffffu, ok);
         if (lane == 0) {
             out[g] = ok ? s : nan("");
-            out_valid[g] = ok ? 1 : 0;
+            out_valid[g] = (ok && bit_get(validity, g)) ? 1 : 0;  // a null row stays null (area / length / x / y do the same)
         }
     }
 }

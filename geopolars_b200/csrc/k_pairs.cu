@@ -695,6 +695,84 @@ __global__ void __launch_bounds__(256) k_distance_generic(int64_t n, Side a, con
     }
 }
 
+// ---- Multi* operands of GeoSeries::distance ----------------------------------------------------------------------
+// geo 0.27 euclidean_distance.rs (recalled), `impl_euclidean_distance_for_iter_geometry!`:
+//     self.iter().map(|g| g.euclidean_distance(target)).fold(T::max_value(), |acc, v| acc.min(v))
+// i.e. the minimum over the members (f64::MAX for an empty collection); min is exact, so the order is irrelevant.
+// Members are addressed through VIEW sides of the single types: MultiPoint -> coordinate index, MultiLineString ->
+// LINESTRING view whose go is the ring_off level, MultiPolygon -> POLYGON view whose go is the part_off level.
+// A member pair on which geo would panic (nearest_neighbor on an empty tree) makes the row invalid.
+__device__ __forceinline__ double point_polygon_distance(const Side &s, int64_t q, double2 p, int lane) {
+    const int64_t r0 = s.go[q], r1 = s.go[q + 1];
+    if (r1 <= r0 || s.ro[r0 + 1] - s.ro[r0] == 0) return 0.0;
+    bool inside = false;
+    int bc = 0;
+    polygon_position(s.xy, s.ro, r0, r1, p, lane, inside, bc);
+    if (bc % 2 == 1 || inside) return 0.0;
+    double acc = 1.7976931348623157e308;
+    for (int64_t h = r0 + 1; h < r1; ++h) acc = fmin(acc, point_ls_distance(s.xy, s.ro[h], s.ro[h + 1] - s.ro[h], p, lane));
+    double ext = 1.7976931348623157e308;
+    const int64_t c0 = s.ro[r0], nn = s.ro[r0 + 1] - c0;
+    for (int64_t i = lane; i < nn - 1; i += 32) ext = fmin(ext, line_segment_distance(p, s.xy[c0 + i], s.xy[c0 + i + 1]));
+    return fmin(acc, warp_min(ext));
+}
+// a, b: single-type views (POINT / LINESTRING / POLYGON), ia / ib: member indices
+__device__ __forceinline__ double member_distance(const Side &a, int64_t ia, const Side &b, int64_t ib, int lane, bool &ok) {
+    const int ca = side_class(a.type), cb = side_class(b.type);
+    if (ca == 0 && cb == 0) return pt_dist(a.xy[ia], b.xy[ib]);
+    if (ca == 0 && cb == 1) return point_ls_distance(b.xy, b.go[ib], b.go[ib + 1] - b.go[ib], a.xy[ia], lane);
+    if (ca == 1 && cb == 0) return point_ls_distance(a.xy, a.go[ia], a.go[ia + 1] - a.go[ia], b.xy[ib], lane);
+    if (ca == 0) return point_polygon_distance(b, ib, a.xy[ia], lane);
+    if (cb == 0) return point_polygon_distance(a, ia, b.xy[ib], lane);
+    const int64_t a0 = a.go[ia], a1 = a.go[ia + 1], b0 = b.go[ib], b1 = b.go[ib + 1];
+    const bool pa = ca == 2, pb = cb == 2;
+    const Chain ea = pa ? (a1 > a0 ? part_ring(a, a0) : Chain{a.xy, 0, false}) : make_line(a.xy, a0, a1);
+    const Chain eb = pb ? (b1 > b0 ? part_ring(b, b0) : Chain{b.xy, 0, false}) : make_line(b.xy, b0, b1);
+    if (!pa && !pb) {  // LineString x LineString: the intersection test comes first (geo), then the tree lookup that may panic
+        if (ls_intersects_ls(ea, ea.n, eb, eb.n, lane)) return 0.0;
+        if (ea.n < 2 || eb.n < 2) {
+            ok = false;
+            return 0.0;
+        }
+        return sqrt(chain_nn_dist2(ea, eb, lane));
+    }
+    if (ea.n < 2 || eb.n < 2) {  // the first chain of each side (the linestring, or the exterior ring) must have a line
+        ok = false;
+        return 0.0;
+    }
+    if (row_intersects(a, ia, b, ib, lane)) return 0.0;
+    double m = 1.7976931348623157e308;
+    if (pa && a1 - a0 > 1 && ring_position(a.xy, a.ro[a0], a.ro[a0 + 1] - a.ro[a0], eb.p[0], lane) == 2) {
+        for (int64_t h = a0 + 1; h < a1; ++h) m = fmin(m, chain_nn_dist2(eb, part_ring(a, h), lane));
+    } else if (pb && b1 - b0 > 1 && ring_position(b.xy, b.ro[b0], b.ro[b0 + 1] - b.ro[b0], ea.p[0], lane) == 2) {
+        for (int64_t h = b0 + 1; h < b1; ++h) m = fmin(m, chain_nn_dist2(ea, part_ring(b, h), lane));
+    } else {
+        m = chain_nn_dist2(ea, eb, lane);
+    }
+    return sqrt(m);
+}
+// one warp per row; am / bm: the geom_off level of a Multi* operand (members [am[r], am[r+1])), NULL for a single type
+__global__ void __launch_bounds__(256) k_distance_multi(int64_t n, Side a, const int64_t *__restrict__ am, const uint8_t *__restrict__ av,
+                                                        Side b, const int64_t *__restrict__ bm, const uint8_t *__restrict__ bv,
+                                                        double *__restrict__ out, uint8_t *__restrict__ out_valid) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        bool ok = bit_get(av, r) && bit_get(bv, r);
+        double d = 1.7976931348623157e308;
+        if (ok) {
+            const int64_t a0 = am ? am[r] : r, a1 = am ? am[r + 1] : r + 1, b0 = bm ? bm[r] : r, b1 = bm ? bm[r + 1] : r + 1;
+            for (int64_t p = a0; p < a1; ++p)
+                for (int64_t q = b0; q < b1; ++q) d = fmin(d, member_distance(a, p, b, q, lane, ok));
+        }
+        if (lane == 0) {
+            out[r] = ok ? d : nan("");
+            if (out_valid) out_valid[r] = ok ? 1 : 0;
+        }
+    }
+}
+
 // impl Contains<Coord> for LineString (interior only: an end point counts only on a closed linestring);
 // MultiLineString: any member.  geo 0.27 contains/line_string.rs, contains/line.rs (recalled).
 __global__ void __launch_bounds__(256) k_lines_contain_point(int64_t n, Side a, const uint8_t *__restrict__ av,
@@ -912,8 +990,11 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
     GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "distance: lengths differ (%lld vs %lld)",
                 (long long)a->n_geoms, (long long)b->n_geoms);
     const int ta = a->type, tb = b->type;
-    bool ok = (ta == GPL_POINT || ta == GPL_LINESTRING || ta == GPL_POLYGON) && (tb == GPL_POINT || tb == GPL_LINESTRING || tb == GPL_POLYGON);
-    GPL_REQUIRE(ok, GPL_ERR_INVALID_TYPE, "distance: unsupported geometry pair %s x %s", type_name(ta), type_name(tb));
+    auto known = [](int t) {
+        return t == GPL_POINT || t == GPL_LINESTRING || t == GPL_POLYGON || t == GPL_MULTIPOINT || t == GPL_MULTILINESTRING || t == GPL_MULTIPOLYGON;
+    };
+    GPL_REQUIRE(known(ta) && known(tb), GPL_ERR_INVALID_TYPE, "distance: unsupported geometry pair %s x %s", type_name(ta), type_name(tb));
+    auto is_multi = [](int t) { return t == GPL_MULTIPOINT || t == GPL_MULTILINESTRING || t == GPL_MULTIPOLYGON; };
     GPL_CUDA(cudaSetDevice(ctx->device));
     int64_t n = a->n_geoms;
     if (n == 0) return GPL_OK;
@@ -930,7 +1011,18 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
         vb = vbytes.p;
     }
     const double2 *axy = reinterpret_cast<const double2 *>(a->xy), *bxy = reinterpret_cast<const double2 *>(b->xy);
-    if (ta == GPL_LINESTRING && tb == GPL_LINESTRING) {
+    if (is_multi(ta) || is_multi(tb)) {  // minimum over the members (geo's impl for iterable geometries)
+        auto view = [](const gpl_array *g, const double2 *xy) {
+            switch (g->type) {
+            case GPL_MULTIPOINT: return Side{GPL_POINT, xy, nullptr, nullptr, nullptr};
+            case GPL_MULTILINESTRING: return Side{GPL_LINESTRING, xy, g->ring_off, nullptr, nullptr};
+            case GPL_MULTIPOLYGON: return Side{GPL_POLYGON, xy, g->part_off, nullptr, g->ring_off};
+            default: return Side{g->type, xy, g->geom_off, g->part_off, g->ring_off};
+            }
+        };
+        GPL_LAUNCH(ctx, k_distance_multi, warp_grid(n, 8), 256, 0, n, view(a, axy), is_multi(ta) ? a->geom_off : nullptr, a->validity,
+                   view(b, bxy), is_multi(tb) ? b->geom_off : nullptr, b->validity, dst, vb);
+    } else if (ta == GPL_LINESTRING && tb == GPL_LINESTRING) {
         Scratch<uint8_t> flag;
         GPL_TRY(flag.get(ctx, (size_t)n));
         GPL_LAUNCH(ctx, k_ls_ls_fast<1>, warp_grid(n, kPairWarps), kPairWarps * 32, 0, n, axy, a->geom_off, a->validity, bxy, b->geom_off,

@@ -776,7 +776,7 @@ static __device__ __noinline__ bool bucket_contains_exact(const EdgeRec *__restr
 // Why a code other than 3 is exact.  Work in cell units: T(v) = (v - lo) * inv as a REAL map; the computed
 // (v - lo) * inv of a double differs from T(v) by at most 2^-31 cells (two roundings of 2^-53 relative, at most
 // 2^20 fine cells per axis), so every double that maps to cell (c, r) lies in the real rectangle
-// Q(c,r) = T^-1([c - e/2, c + 1 + e/2] x [r - e/2, r + 1 + e/2]) with e = 1e-6.  raster_mark_edge marks every cell
+// Q(c,r) = T^-1([c - e/2, c + 1 + e/2] x [r - e/2, r + 1 + e/2]) with e = 1e-6.  raster_mark_row marks every cell
 // whose e-inflated square meets the segment (row by row, with the slack analysed there), for every ring segment of
 // every valid part — including the closing segment geo's Polygon::new adds and 1-coordinate rings.  A cell that is
 // not marked by part P therefore has no point of P's rings in Q(c,r): Q is convex, so it lies in one face of each
@@ -795,82 +795,36 @@ __device__ __forceinline__ void raster_or_span(uint32_t *__restrict__ raster, in
         atomicOr(row + w, rep & m);
     }
 }
-// mark (code 3) every fine cell within 1e-6 cells of the segment s-e.  Returns false when the segment has a
-// non-finite coordinate in cell units (the caller then marks the whole grid).
-__device__ bool raster_mark_edge(uint32_t *__restrict__ raster, const GridParams &g, double2 s, double2 e) {
-    // the arguments of fine_index, as the query kernel computes them
-    const double tsx = (s.x - g.x0) * g.inv_fw, tsy = (s.y - g.y0) * g.inv_fh;
-    const double tex = (e.x - g.x0) * g.inv_fw, tey = (e.y - g.y0) * g.inv_fh;
-    if (!(isfinite(tsx) && isfinite(tsy) && isfinite(tex) && isfinite(tey))) return false;
+// One row of raster_mark: mark (code 3) every fine cell of row r within 1e-6 cells of the segment whose images in cell
+// units are (tsx,tsy)-(tex,tey).
+__device__ __forceinline__ void raster_mark_row(uint32_t *__restrict__ raster, const GridParams &g, int32_t r, double tsx, double tsy,
+                                                double tex, double tey) {
     const double eps = 1e-6;
-    const double ylo = fmin(tsy, tey), yhi = fmax(tsy, tey);
-    const int32_t r0 = min(max(__double2int_rd(ylo - eps), 0), g.fgy - 1), r1 = min(max(__double2int_rd(yhi + eps), 0), g.fgy - 1);
     const double dy = tey - tsy, dx = tex - tsx;
-    // nearly horizontal in cell units: take the whole x-range on each of the (at most 3) rows
-    const bool flat = fabs(dy) < 1e-3;
-    const double inv_dy = flat ? 0.0 : 1.0 / dy;
-    for (int32_t r = r0; r <= r1; ++r) {
-        double xa, xb;
-        if (flat) {
-            xa = fmin(tsx, tex), xb = fmax(tsx, tex);
-        } else {
-            // parameter range of the segment inside the slab [r - eps, r + 1 + eps].  Errors: the endpoints are within
-            // 2^-30 of their true images and so is dy, i.e. lambda is off by at most 4 * 2^-30 / |dy| — 270 times
-            // smaller than the eps / |dy| the slab was widened by; x(lambda) adds a few 2^-32.  The 2e-6 margin below
-            // covers the rest.
-            double l0 = ((double)r - eps - tsy) * inv_dy, l1 = ((double)r + 1.0 + eps - tsy) * inv_dy;
-            if (l0 > l1) {
-                const double t = l0;
-                l0 = l1, l1 = t;
-            }
-            l0 = fmax(l0, 0.0), l1 = fmin(l1, 1.0);
-            if (l0 > l1) continue;  // a clamped border row the segment does not reach (no query point maps there)
-            xa = tsx + l0 * dx, xb = tsx + l1 * dx;
-            if (xa > xb) {
-                const double t = xa;
-                xa = xb, xb = t;
-            }
+    double xa, xb;
+    if (fabs(dy) < 1e-3) {  // nearly horizontal in cell units: the whole x-range on each of the (at most 3) rows
+        xa = fmin(tsx, tex), xb = fmax(tsx, tex);
+    } else {
+        // parameter range of the segment inside the slab [r - eps, r + 1 + eps].  Errors: the endpoints are within
+        // 2^-30 of their true images and so is dy, i.e. lambda is off by at most 4 * 2^-30 / |dy| — 270 times
+        // smaller than the eps / |dy| the slab was widened by; x(lambda) adds a few 2^-32.  The 2e-6 margin below
+        // covers the rest.
+        const double inv_dy = 1.0 / dy;
+        double l0 = ((double)r - eps - tsy) * inv_dy, l1 = ((double)r + 1.0 + eps - tsy) * inv_dy;
+        if (l0 > l1) {
+            const double t = l0;
+            l0 = l1, l1 = t;
         }
-        const int32_t c0 = min(max(__double2int_rd(xa - 2e-6), 0), g.fgx - 1), c1 = min(max(__double2int_rd(xb + 2e-6), 0), g.fgx - 1);
-        raster_or_span(raster, g.wpr, r, c0, c1, 3u);
-    }
-    return true;
-}
-// one warp per part, lanes over the edge slots of its rings
-__device__ void ph_raster_mark(const BuildArgs &a, const GridParams &g) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
-    if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;  // degenerate axis: the raster was filled with 3 (fill kernel, T0)
-    for (int64_t p = warp; p < a.P; p += nwarps) {
-        const PartHeader h = a.hdr[p];
-        if (!(h.flags & 2)) continue;
-        int64_t r0, r1;
-        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
-        bool irregular = false;
-        for (int64_t r = r0; r < r1; ++r) {
-            const int64_t c0 = a.ring_off[r], c1 = a.ring_off[r + 1];
-            for (int64_t c = c0 + lane; c < c1; c += 32) {
-                double2 s, e;
-                if (!edge_of_slot(a.xy, c, c0, c1, s, e)) continue;
-                // an edge with a NaN coordinate never satisfies geo's comparisons (NaN ordinate) or never yields a
-                // non-zero / zero orientation (NaN abscissa): it contributes nothing and bounds no face
-                if (isnan(s.x) || isnan(s.y) || isnan(e.x) || isnan(e.y)) continue;
-                if (!raster_mark_edge(a.raster, g, s, e)) irregular = true;
-            }
-        }
-        if (__any_sync(0xffffffffu, irregular)) {  // infinite coordinates: every cell of the grid takes the walk
-            for (int32_t fy = lane; fy < g.fgy; fy += 32) raster_or_span(a.raster, g.wpr, fy, 0, g.fgx - 1, 3u);
+        l0 = fmax(l0, 0.0), l1 = fmin(l1, 1.0);
+        if (l0 > l1) return;  // a clamped border row the segment does not reach (no query point maps there)
+        xa = tsx + l0 * dx, xb = tsx + l1 * dx;
+        if (xa > xb) {
+            const double t = xa;
+            xa = xb, xb = t;
         }
     }
-}
-// Polygon::contains(rep) for one part from the f64 bucket records (exact)
-__device__ __forceinline__ bool part_contains_exact(const BuildArgs &a, const PartHeader &h, const int32_t *__restrict__ bstart,
-                                                    double px, double py) {
-    if (!(px >= h.xmin && px <= h.xmax && py >= h.ymin && py <= h.ymax)) return false;
-    const int32_t b = mono_index(py, h.by0, h.inv_h, h.n_buckets);
-    const int32_t e0 = bstart[h.bucket_base + b], e1 = bstart[h.bucket_base + b + 1];
-    return bucket_contains_exact(a.entries, a.entry_ring, (h.flags & 1) != 0, e0, e1, px, py);
+    const int32_t c0 = min(max(__double2int_rd(xa - 2e-6), 0), g.fgx - 1), c1 = min(max(__double2int_rd(xb + 2e-6), 0), g.fgx - 1);
+    raster_or_span(raster, g.wpr, r, c0, c1, 3u);
 }
 // raster code of "strictly inside part `part` only" in coarse cell (cx, cy): 1 / 2 for candidate #0 / #1, else 3
 __device__ __forceinline__ uint32_t raster_rank_code(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
@@ -881,55 +835,142 @@ __device__ __forceinline__ uint32_t raster_rank_code(const BuildArgs &a, const G
     if (s + 1 < e && a.items[s + 1] == part) return 2u;
     return 3u;
 }
-// Interior fill: one warp per part, lanes over the fine rows of its bbox; each lane walks its row left to right,
-// classifies the first cell of every run of unmarked cells with one exact test and ORs the run's inside code in.
-__device__ void ph_raster_fill(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
-                               const int32_t *__restrict__ bstart) {
-    const int lane = threadIdx.x & 31;
+// OR the inside code of `part` over cells [lo, hi] of fine row fy (the code depends on the coarse column)
+__device__ __forceinline__ void raster_fill_span(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
+                                                 int32_t fy, int32_t lo, int32_t hi, int32_t part) {
+    for (int32_t cc = lo >> g.rs; cc <= (hi >> g.rs); ++cc) {
+        const int32_t x0 = max(lo, cc << g.rs), x1 = min(hi, ((cc + 1) << g.rs) - 1);
+        raster_or_span(a.raster, g.wpr, fy, x0, x1, raster_rank_code(a, g, cell_start, cc, fy >> g.rs, part));
+    }
+}
+
+// The raster of one part, built by one warp in chunks of 32 fine rows of the part's bbox:
+//   edge-major: every lane takes edges of the part's rings; for every row of the chunk an edge comes near, it marks the
+//               cells along the edge (code 3) and, when the edge straddles the row's CENTRE LINE y = ry (geo's half-open
+//               rule: upward s.y <= ry < e.y, downward e.y <= ry < s.y), records the crossing cell, direction and ring
+//               in the row's list in shared memory;
+//   row-major : every lane takes one row, sorts its crossings by cell and ORs the inside code over the cells strictly
+//               between consecutive crossings whose winding numbers say Inside (exterior ring winds, no hole winds).
+// Why this is exact for every cell that keeps a code other than 3: such a cell is not marked, so (argument above) one
+// representative decides it — take the cell centre (c + 1/2, ry).  geo's winding number of a ring at that point counts the
+// ring's upward edges the point is left of minus the downward edges it is right of, i.e. the straddling edges whose crossing
+// with y = ry lies at larger x.  The true crossing and the computed one (lambda is off by < 2^-29 / |dy|, far less than
+// the half slab height the marks cover) both lie in the contiguous run of cells this edge marked on this row; an unmarked
+// cell is outside that run, hence on the same side of both: comparing CELL indices orders the centre and the crossing
+// exactly.  Everything the lists cannot hold (more than kRowCross crossings in a row, a row whose centre does not map
+// back to it) is coded 3 over the part's whole column range, which is always safe.
+constexpr int kRowCross = 8;
+constexpr int kRowStride = kRowCross + 1;  // odd stride: the 32 lists of a chunk do not collide on banks
+struct RasterSmem {
+    int32_t cnt[kBuildThreads / 32][32];
+    uint32_t list[kBuildThreads / 32][32 * kRowStride];  // cell (20 bits) | down (bit 20) | ring (bits 21..31, saturated)
+};
+__device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start, RasterSmem &sm) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
-    if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;
+    if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;  // degenerate axis: the raster was filled with 3 (fill kernel, T0)
+    int32_t *cnt = sm.cnt[wid];
+    uint32_t *list = sm.list[wid];
     for (int64_t p = warp; p < a.P; p += nwarps) {
         const PartHeader h = a.hdr[p];
         if (!(h.flags & 2)) continue;
+        int64_t r0, r1;
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
         const int32_t fx0 = fine_index(h.xmin, g.x0, g.inv_fw, g.fgx), fx1 = fine_index(h.xmax, g.x0, g.inv_fw, g.fgx);
         const int32_t fy0 = fine_index(h.ymin, g.y0, g.inv_fh, g.fgy), fy1 = fine_index(h.ymax, g.y0, g.inv_fh, g.fgy);
-        for (int32_t fy = fy0 + lane; fy <= fy1; fy += 32) {
-            const double ry = g.y0 + ((double)fy + 0.5) / g.inv_fh;
-            const bool row_ok = fine_index(ry, g.y0, g.inv_fh, g.fgy) == fy;
-            uint32_t *row = a.raster + (int64_t)fy * g.wpr;
-            bool in_run = false, inside = false;
-            int32_t cur_cc = -1, wcur = fx0 >> 4;
-            uint32_t code = 3u, wmask = 0u, wval = __ldcg(row + wcur);
-            for (int32_t fx = fx0; fx <= fx1; ++fx) {
-                const int32_t w = fx >> 4, sh = (fx & 15) * 2;
-                if (w != wcur) {
-                    if (wmask) atomicOr(row + wcur, wmask);
-                    wmask = 0u, wcur = w, wval = __ldcg(row + w);
-                }
-                if (((wval >> sh) & 3u) == 3u) {  // a ring of some part passes here: the run ends
-                    in_run = false;
-                    continue;
-                }
-                if (!in_run) {
-                    const double rx = g.x0 + ((double)fx + 0.5) / g.inv_fw;
-                    if (!row_ok || fine_index(rx, g.x0, g.inv_fw, g.fgx) != fx) {  // no representative: walk
-                        wmask |= 3u << sh;
+        bool irregular = false;
+        for (int32_t ra = fy0; ra <= fy1; ra += 32) {
+            const int32_t rb = min(ra + 31, fy1);
+            cnt[lane] = 0;
+            __syncwarp();
+            // ---- edge-major: marks + centre-line crossings of the rows [ra, rb]
+            for (int64_t r = r0; r < r1; ++r) {
+                const int64_t c0 = a.ring_off[r], c1 = a.ring_off[r + 1];
+                const uint32_t ring_tag = (uint32_t)((r - r0) < 2047 ? (r - r0) : 2047) << 21;
+                for (int64_t c = c0 + lane; c < c1; c += 32) {
+                    double2 s, e;
+                    if (!edge_of_slot(a.xy, c, c0, c1, s, e)) continue;
+                    // an edge with a NaN coordinate never satisfies geo's comparisons (NaN ordinate) or never yields a
+                    // non-zero / zero orientation (NaN abscissa): it contributes nothing and bounds no face
+                    if (isnan(s.x) || isnan(s.y) || isnan(e.x) || isnan(e.y)) continue;
+                    // the arguments of fine_index, as the query kernel computes them
+                    const double tsx = (s.x - g.x0) * g.inv_fw, tsy = (s.y - g.y0) * g.inv_fh;
+                    const double tex = (e.x - g.x0) * g.inv_fw, tey = (e.y - g.y0) * g.inv_fh;
+                    if (!(isfinite(tsx) && isfinite(tsy) && isfinite(tex) && isfinite(tey))) {
+                        irregular = true;
                         continue;
                     }
-                    inside = part_contains_exact(a, h, bstart, rx, ry);
-                    in_run = true;
-                }
-                if (inside) {
-                    const int32_t cc = fx >> g.rs;
-                    if (cc != cur_cc) {
-                        cur_cc = cc;
-                        code = raster_rank_code(a, g, cell_start, cc, fy >> g.rs, (int32_t)p);
+                    const double ylo = fmin(tsy, tey), yhi = fmax(tsy, tey);
+                    const int32_t er0 = max(min(max(__double2int_rd(ylo - 1e-6), 0), g.fgy - 1), ra);
+                    const int32_t er1 = min(min(max(__double2int_rd(yhi + 1e-6), 0), g.fgy - 1), rb);
+                    for (int32_t row = er0; row <= er1; ++row) {
+                        raster_mark_row(a.raster, g, row, tsx, tsy, tex, tey);
+                        const double ry = g.y0 + ((double)row + 0.5) / g.inv_fh;
+                        const bool up = s.y <= ry && e.y > ry, down = s.y > ry && e.y <= ry;
+                        if (up || down) {
+                            const double tdy = tey - tsy, try_ = (ry - g.y0) * g.inv_fh;
+                            double lam = tdy != 0.0 ? (try_ - tsy) / tdy : 0.0;
+                            lam = fmin(fmax(lam, 0.0), 1.0);
+                            const int32_t cj = min(max(__double2int_rd(tsx + lam * (tex - tsx)), 0), g.fgx - 1);
+                            const int32_t slot = atomicAdd(&cnt[row - ra], 1);
+                            if (slot < kRowCross) list[(row - ra) * kRowStride + slot] = (uint32_t)cj | (down ? (1u << 20) : 0u) | ring_tag;
+                        }
                     }
-                    wmask |= code << sh;
                 }
             }
-            if (wmask) atomicOr(row + wcur, wmask);
+            __syncwarp();
+            // ---- row-major: one lane per row of the chunk
+            const int32_t fy = ra + lane;
+            if (fy <= rb) {
+                const int32_t n = cnt[lane];
+                const double ry = g.y0 + ((double)fy + 0.5) / g.inv_fh;
+                uint32_t *L = list + lane * kRowStride;
+                if (n > kRowCross || fine_index(ry, g.y0, g.inv_fh, g.fgy) != fy) {
+                    raster_or_span(a.raster, g.wpr, fy, fx0, fx1, 3u);  // cannot be classified from the list: walk
+                } else if (n > 0) {
+                    for (int i = 1; i < n; ++i) {  // insertion sort by cell (the low 20 bits)
+                        const uint32_t v = L[i];
+                        int j = i - 1;
+                        while (j >= 0 && (L[j] & 0xfffffu) > (v & 0xfffffu)) {
+                            L[j + 1] = L[j];
+                            --j;
+                        }
+                        L[j + 1] = v;
+                    }
+                    for (int k = 1; k < n; ++k) {  // cells strictly between crossing k-1 and crossing k
+                        const int32_t lo = (int32_t)(L[k - 1] & 0xfffffu) + 1, hi = (int32_t)(L[k] & 0xfffffu) - 1;
+                        if (lo > hi) continue;
+                        // winding numbers at the interval = crossings to its right (entries k..n-1), ring by ring
+                        int wn_ext = 0;
+                        bool in_hole = false;
+                        for (int j = k; j < n; ++j) {
+                            const uint32_t ring = L[j] >> 21;
+                            const int dir = (L[j] & (1u << 20)) ? -1 : 1;
+                            if (ring == 0u) {
+                                wn_ext += dir;
+                            } else {
+                                bool first = true;  // sum this hole once, at its first entry
+                                for (int i = k; i < j; ++i) first = first && (L[i] >> 21) != ring;
+                                if (first) {
+                                    int w = 0;
+                                    for (int i = j; i < n; ++i) w += ((L[i] >> 21) == ring) ? ((L[i] & (1u << 20)) ? -1 : 1) : 0;
+                                    in_hole = in_hole || w != 0;
+                                }
+                            }
+                        }
+                        // ring indices saturate at 2047: a part with more rings cannot separate its holes — walk
+                        bool saturated = false;
+                        for (int j = k; j < n; ++j) saturated = saturated || (L[j] >> 21) == 2047u;
+                        if (saturated) raster_or_span(a.raster, g.wpr, fy, lo, hi, 3u);
+                        else if (wn_ext != 0 && !in_hole) raster_fill_span(a, g, cell_start, fy, lo, hi, (int32_t)p);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (__any_sync(0xffffffffu, irregular)) {  // infinite coordinates: every cell of the grid takes the walk
+            for (int32_t fy = lane; fy < g.fgy; fy += 32) raster_or_span(a.raster, g.wpr, fy, 0, g.fgx - 1, 3u);
         }
     }
 }
@@ -975,6 +1016,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
     cg::grid_group grid = cg::this_grid();
     __shared__ int64_t sm_scan[kBuildThreads / 32 + 1];
     __shared__ int64_t sm_prefix[kMaxBuildCtas];
+    __shared__ RasterSmem sm_raster;
     const GridParams g = *a.gp;
     const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     const bool degenerate = g.inv_fw == 0.0 || g.inv_fh == 0.0;
@@ -1027,11 +1069,10 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
     ph_part_recs(a);
     for (int64_t b = tid; b < a.n_buckets; b += nth) a.bucket_range[b] = make_int2(bstart[b], bstart[b + 1]);
     ph_materialise(a, bstart);
-    ph_raster_mark(a, g);
+    ph_raster(a, g, cell_start, sm_raster);
     grid.sync();
-    // T5: FP32 lists, raster interior
+    // T5: FP32 lists
     ph_fast_fill(a, bstart);
-    ph_raster_fill(a, g, cell_start, bstart);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1422,8 +1463,8 @@ __device__ __forceinline__ void ld256s(const double2 *p, double2 &a, double2 &b)
 }
 // HIST: per-polygon hit counts (config 4's all-reduce input) in the same pass: 32-bit bins privatised per CTA in shared
 // memory behind the queues, flushed with one 64-bit global atomic per non-zero bin when the CTA retires.
-template <bool LEAN, bool HIST>
-__global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
+template <bool LEAN, bool HIST, int MINB>
+__global__ void __launch_bounds__(kQueryThreads, MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
                                                                                   const uint8_t *__restrict__ pts_validity, int64_t n_pts,
                                                                                   int32_t *__restrict__ first_id, int32_t *__restrict__ count,
                                                                                   unsigned long long *__restrict__ n_deferred,
@@ -1667,15 +1708,15 @@ static int query_grid(int64_t n, bool lean = false) {
 }
 // streaming kernel: exactly the resident CTAs (persistent warps, one tile of 128 points per warp and iteration)
 constexpr int32_t kHistFuseMaxBins = 12288;  // 48 KB of bins per CTA: three CTAs per SM still fit next to the queues
-template <bool LEAN, bool HIST>
+template <bool LEAN, bool HIST, int MINB>
 static int stream_grid(int64_t n, size_t smem_bytes) {
     static size_t attr_bytes = 0;
     if (smem_bytes > attr_bytes) {
-        cudaFuncSetAttribute(k_pip_stream<LEAN, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_pip_stream<LEAN, HIST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         attr_bytes = smem_bytes;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN, HIST>, kQueryThreads, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN, HIST, MINB>, kQueryThreads, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
     (void)cudaGetLastError();
     static const int cap = env_int("GPL_PIP_STREAM_CTAS_PER_SM", 0);
     const int per_sm = cap > 0 ? std::min(cap, occ) : occ;
@@ -1686,16 +1727,24 @@ template <bool LEAN, bool HIST>
 static void launch_stream(const IndexView &v, const double2 *pts, const uint8_t *val, int64_t m, int32_t *first, int32_t *cnt,
                           const gpl_pip_index *idx, int vec_ok, unsigned long long *hist, int32_t n_bins, cudaStream_t stream) {
     const size_t smem = sizeof(StreamSmem) + (HIST ? sizeof(unsigned int) * (size_t)n_bins : 0);
-    k_pip_stream<LEAN, HIST><<<stream_grid<LEAN, HIST>(m, smem), kQueryThreads, smem, stream>>>(v, pts, val, m, first, cnt, idx->n_deferred,
-                                                                                             idx->deferred_list, idx->deferred_cap, vec_ok, hist,
-                                                                                             n_bins);
+    // resident CTAs per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers)
+    static const int minb = env_int("GPL_PIP_STREAM_MINB", GPL_PIP_STREAM_MINB);
+    if (minb >= 4)
+        k_pip_stream<LEAN, HIST, 4><<<stream_grid<LEAN, HIST, 4>(m, smem), kQueryThreads, smem, stream>>>(
+            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
+    else
+        k_pip_stream<LEAN, HIST, 3><<<stream_grid<LEAN, HIST, 3>(m, smem), kQueryThreads, smem, stream>>>(
+            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
 }
 
 // hist (optional, device, n_geoms u64): += number of points whose first containing row is that polygon
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
               int32_t *first_dev, int32_t *count_dev, cudaStream_t stream, unsigned long long *hist = nullptr) {
     if (n == 0) return GPL_OK;
-    const bool fuse_hist = hist != nullptr && idx->n_geoms <= kHistFuseMaxBins;
+    // Per-polygon counts: a separate pass over the id column (k_histogram: 0.1 ms per 100 M ids) by default; the variant
+    // fused into the streaming kernel (shared-memory bins) measured slower on config 2 (+0.22 ms) and is opt-in.
+    static const bool fuse_enabled = env_int("GPL_PIP_FUSE_HIST", 0) != 0;
+    const bool fuse_hist = fuse_enabled && hist != nullptr && idx->n_geoms <= kHistFuseMaxBins;
     const double2 *pts = reinterpret_cast<const double2 *>(pts_dev);
     const IndexView v = view_of(idx);
     static const bool legacy = env_int("GPL_PIP_LEGACY", 0) != 0;  // round-1 kernel: every point walks (A/B measurements)

@@ -204,8 +204,9 @@ int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **out);
  * tolerance <= 0 returns the input coordinates.  Outer offsets and validity are shared with the input. */
 int gpl_simplify(gpl_ctx *ctx, const gpl_array *in, double tolerance, gpl_array **out);
 /* GeoSeries::distance (geoseries.rs:141-146), row-wise 1:1; out[n] f64, out_validity bitmap
- * (may be NULL).  Pairs: any of Point / LineString / Polygon on either side (geo EuclideanDistance);
- * other types -> GPL_ERR_INVALID_TYPE.  A row without a single segment where geo needs one is null. */
+ * (may be NULL).  Pairs: any of Point / LineString / Polygon / MultiPoint / MultiLineString / MultiPolygon on
+ * either side (geo EuclideanDistance; a Multi* operand is the minimum over its members, f64::MAX when it has none).
+ * A row without a single segment where geo needs one (it would panic) is null. */
 int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, double *out, uint8_t *out_validity, int mem);
 /* row-wise intersects (call sites spatial_index.rs:102-123 / geo Intersects); Arrow bitmap out.  Every pair of
  * Point, MultiPoint, LineString, MultiLineString, Polygon, MultiPolygon arrays; null row -> false */

@@ -1094,36 +1094,68 @@ static double polygon_polygon_distance(const og_array *a, int64_t ia, const og_a
     }
     return chain_nn_distance(&ea, &eb);
 }
+/* distance between two SINGLE geometries (Point / LineString / Polygon views, member indices ia / ib) */
+static double single_distance(const og_array *a, int64_t ia, const og_array *b, int64_t ib, int *ok) {
+    int ta = a->type, tb = b->type;
+    if (ta == OG_POINT && tb == OG_POINT) return pt_dist(a->xy + 2 * ia, b->xy + 2 * ib);
+    if (ta == OG_POINT && tb == OG_LINESTRING) return point_ls_distance(a->xy + 2 * ia, b->xy + 2 * b->geom_off[ib], b->geom_off[ib + 1] - b->geom_off[ib]);
+    if (ta == OG_LINESTRING && tb == OG_POINT) return point_ls_distance(b->xy + 2 * ib, a->xy + 2 * a->geom_off[ia], a->geom_off[ia + 1] - a->geom_off[ia]);
+    if (ta == OG_LINESTRING && tb == OG_LINESTRING)
+        return ls_ls_distance(a->xy + 2 * a->geom_off[ia], a->geom_off[ia + 1] - a->geom_off[ia], b->xy + 2 * b->geom_off[ib],
+                              b->geom_off[ib + 1] - b->geom_off[ib], ok);
+    if (ta == OG_POINT && tb == OG_POLYGON) return point_polygon_distance(a->xy + 2 * ia, b, ib);
+    if (ta == OG_POLYGON && tb == OG_POINT) return point_polygon_distance(b->xy + 2 * ib, a, ia);
+    if (ta == OG_LINESTRING && tb == OG_POLYGON) {
+        chain_t ls = mk_line(a->xy, a->geom_off[ia], a->geom_off[ia + 1]);
+        return ls_polygon_distance(&ls, b, ib, ok);
+    }
+    if (ta == OG_POLYGON && tb == OG_LINESTRING) {
+        chain_t ls = mk_line(b->xy, b->geom_off[ib], b->geom_off[ib + 1]);
+        return ls_polygon_distance(&ls, a, ia, ok);
+    }
+    return polygon_polygon_distance(a, ia, b, ib, ok);
+}
+/* Members of a Multi* row as single geometries: a VIEW of the same buffers whose geom_off is the next offset level
+ * (MultiPoint -> points, MultiLineString -> its lines via ring_off, MultiPolygon -> its polygons via part_off). */
+static og_array member_view(const og_array *a) {
+    og_array v = *a;
+    v.valid = NULL;
+    switch (a->type) {
+    case OG_MULTIPOINT: v.type = OG_POINT, v.geom_off = NULL; break;
+    case OG_MULTILINESTRING: v.type = OG_LINESTRING, v.geom_off = a->ring_off, v.ring_off = NULL; break;
+    case OG_MULTIPOLYGON: v.type = OG_POLYGON, v.geom_off = a->part_off, v.part_off = NULL; break;
+    default: break;
+    }
+    return v;
+}
+static void member_range(const og_array *a, int64_t i, int64_t *lo, int64_t *hi) {
+    if (a->type == OG_MULTIPOINT || a->type == OG_MULTILINESTRING || a->type == OG_MULTIPOLYGON) *lo = a->geom_off[i], *hi = a->geom_off[i + 1];
+    else *lo = i, *hi = i + 1;
+}
+/* GeoSeries::distance (geoseries.rs:141-146) row-wise.  Multi* operands: geo 0.27 euclidean_distance.rs (recalled)
+ * `impl_euclidean_distance_for_iter_geometry!`: self.iter().map(|g| g.euclidean_distance(target))
+ * .fold(T::max_value(), |acc, v| acc.min(v)) — the minimum over the members, f64::MAX for an empty collection; a member
+ * pair on which geo would panic (nearest_neighbor on an empty tree) makes the row invalid (NaN). */
 int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int threads) {
     int nt = resolve_threads(threads);
     (void)nt;
-    int ta = a->type, tb = b->type;
-    int supported = (ta == OG_POINT || ta == OG_LINESTRING || ta == OG_POLYGON) && (tb == OG_POINT || tb == OG_LINESTRING || tb == OG_POLYGON);
-    if (!supported || a->n != b->n) return -1;
+    if (a->n != b->n) return -1;
+    const og_array va = member_view(a), vb = member_view(b);
 #pragma omp parallel for num_threads(nt) schedule(dynamic, 1024)
     for (int64_t i = 0; i < a->n; ++i) {
         double v = NAN;
         if (is_valid(a, i) && is_valid(b, i)) {
             int ok = 1;
-            if (ta == OG_POINT && tb == OG_POINT) v = pt_dist(a->xy + 2 * i, b->xy + 2 * i);
-            else if (ta == OG_POINT && tb == OG_LINESTRING)
-                v = point_ls_distance(a->xy + 2 * i, b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i]);
-            else if (ta == OG_LINESTRING && tb == OG_POINT)
-                v = point_ls_distance(b->xy + 2 * i, a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i]);
-            else if (ta == OG_LINESTRING && tb == OG_LINESTRING)
-                v = ls_ls_distance(a->xy + 2 * a->geom_off[i], a->geom_off[i + 1] - a->geom_off[i],
-                                   b->xy + 2 * b->geom_off[i], b->geom_off[i + 1] - b->geom_off[i], &ok);
-            else if (ta == OG_POINT && tb == OG_POLYGON) v = point_polygon_distance(a->xy + 2 * i, b, i);
-            else if (ta == OG_POLYGON && tb == OG_POINT) v = point_polygon_distance(b->xy + 2 * i, a, i);
-            else if (ta == OG_LINESTRING && tb == OG_POLYGON) {
-                chain_t ls = mk_line(a->xy, a->geom_off[i], a->geom_off[i + 1]);
-                v = ls_polygon_distance(&ls, b, i, &ok);
-            } else if (ta == OG_POLYGON && tb == OG_LINESTRING) {
-                chain_t ls = mk_line(b->xy, b->geom_off[i], b->geom_off[i + 1]);
-                v = ls_polygon_distance(&ls, a, i, &ok);
-            } else
-                v = polygon_polygon_distance(a, i, b, i, &ok);
-            (void)ok;
+            int64_t a0, a1, b0, b1;
+            member_range(a, i, &a0, &a1);
+            member_range(b, i, &b0, &b1);
+            v = 1.7976931348623157e308;
+            for (int64_t p = a0; p < a1; ++p)
+                for (int64_t q = b0; q < b1; ++q) {
+                    double d = single_distance(&va, p, &vb, q, &ok);
+                    v = fmin(v, d);
+                }
+            if (!ok) v = NAN;
         }
         out[i] = v;
     }

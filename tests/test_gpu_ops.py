@@ -220,11 +220,12 @@ def test_point_distances_and_rowwise_contains(ctx, og, conv):
     got = E.contains(dS, ctx.upload(pts_in))
     want = np.array([og.contains_point(conv(S), i, *pts_in.xy[i]) for i in range(n)])
     assert np.array_equal(got, want) and want.any()
-    from geopolars_b200 import MismatchedGeometry, ShapeError
+    from geopolars_b200 import ShapeError
 
     assert (E.distance(dS, dS)[0] == 0.0).all()  # Polygon x Polygon is on the path (k_distance_generic)
-    with pytest.raises(MismatchedGeometry):  # Multi* distance is not
-        E.distance(dS, ctx.upload(GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, [[(0.0, 0.0)]] * n)))
+    # Multi* operands: the minimum over the members (test_gpu_predicates.py::test_distance_every_type_pair)
+    dmp, ok = E.distance(dS, ctx.upload(GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, [[(0.0, 0.0)]] * n)))
+    assert ok.all() and rel_close(dmp, og.distance_rowwise(conv(S), conv(GeoArrowArray.points(np.zeros((n, 2)))), threads=0), TOL)
     with pytest.raises(ShapeError):
         E.distance(dP, ctx.upload(GeoArrowArray.points(np.zeros((3, 2)))))
 

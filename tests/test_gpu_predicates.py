@@ -38,6 +38,59 @@ def test_intersects_every_type_pair(ctx, og, conv, ka, kb):
     assert 0 < want.sum() < n and not got[5]
 
 
+@pytest.mark.parametrize("ka", shapes.KINDS)
+@pytest.mark.parametrize("kb", shapes.KINDS)
+def test_distance_every_type_pair(ctx, og, conv, ka, kb):
+    """GeoSeries::distance (geoseries.rs:141-146) over every pair of GeoArrow types; Multi* = minimum over the members
+    (geo's impl for iterable geometries), empty collection -> f64::MAX, geo-would-panic rows -> null.  The reference's own
+    datasets (nybb, naturalearth_lowres) are MultiPolygon columns."""
+    rng = np.random.default_rng(zlib.crc32(f"d{ka}x{kb}".encode()))
+    n = 500
+    rb = shapes.random_rows(rng, kb, n)
+    ra = shapes.plant_touching(rng, ka, shapes.random_rows(rng, ka, n), kb, rb)
+    ra[5] = None
+    ga, gb = GeoArrowArray.from_shapes(T[ka], ra), GeoArrowArray.from_shapes(T[kb], rb)
+    want = og.distance_rowwise(conv(ga), conv(gb), threads=0)
+    got, valid = engine.distance(ctx.upload(ga), ctx.upload(gb))
+    ok = ~np.isnan(want)
+    assert np.array_equal(valid, ok) and not valid[5]
+    assert rel_close(got[ok], want[ok], 1e-9)
+    assert (want[ok] == 0.0).any() and (want[ok] > 0.0).any()
+    zero = ok & (want == 0.0)
+    assert (got[zero] == 0.0).all()  # intersecting rows are exactly 0, not merely small
+
+
+def test_distance_multipolygon_datasets(ctx, og, conv):
+    """the reference's bundled MultiPolygon columns against themselves shifted by one row, and against their centroids"""
+    import os
+
+    from geopolars_b200 import engine as E
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "nybb.npz"), allow_pickle=True)
+    from test_oracle_cpu import load
+
+    for name in ("nybb", "naturalearth_lowres"):
+        arr, _ = load(name)
+        d = ctx.upload(arr)
+        n = len(arr)
+        perm = np.roll(np.arange(n), 1)
+        shifted = GeoArrowArray.from_shapes(arr.type, [None] * 0) if n == 0 else None
+        # row-rolled copy built on the host from the nested lists
+        rows = arr.to_shapes() if hasattr(arr, "to_shapes") else None
+        if rows is None:
+            pytest.skip("GeoArrowArray.to_shapes unavailable")
+        rolled = GeoArrowArray.from_shapes(arr.type, [rows[i] for i in perm])
+        want = og.distance_rowwise(conv(arr), conv(rolled), threads=0)
+        got, valid = E.distance(d, ctx.upload(rolled))
+        ok = ~np.isnan(want)
+        assert np.array_equal(valid, ok) and rel_close(got[ok], want[ok], 1e-9)
+        cen = E.centroid(d)
+        cw, cv = og.centroid(conv(arr))
+        want_c = og.distance_rowwise(conv(arr), conv(GeoArrowArray.points(cw)), threads=0)
+        got_c, _ = E.distance(d, cen)
+        assert rel_close(got_c, want_c, 1e-9)
+
+
 def test_polygon_pairs_against_exact_rational_referee(ctx):
     from oracle import exact
 
