@@ -134,6 +134,11 @@ SIGNATURES = {
     "gpl_y": (_INT, [_P, _P, _P, _INT]),
     "gpl_exterior": (_INT, [_P, _P, C.POINTER(_P)]),
     "gpl_explode": (_INT, [_P, _P, C.POINTER(_P)]),
+    "gpl_contains_polygon": (_INT, [_P, _P, _P, _P, _INT]),
+    "gpl_spatial_join": (_INT, [_P, _P, _P, _INT, C.POINTER(_P)]),
+    "gpl_pairs_count": (_I64, [_P]),
+    "gpl_pairs_copy": (_INT, [_P, _P, _P, _P, _INT]),
+    "gpl_pairs_free": (None, [_P]),
     "gpl_envelope_query": (_INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, _INT, _P, _INT]),
     "gpl_pip_index_build": (_INT, [_P, _P, C.POINTER(_P)]),
     "gpl_pip_index_free": (None, [_P]),
@@ -143,6 +148,7 @@ SIGNATURES = {
     "gpl_contains_join_counts": (_INT, [_P, _P, _P, _I64, _P, _P, _INT]),
     "gpl_contains_join_array": (_INT, [_P, _P, _P, _P, _P, _INT]),
     "gpl_contains_join_pairs": (_INT, [_P, _P, _P, _I64, _P, _P, C.POINTER(_I64), _INT]),
+    "gpl_contains_join_pairs_array": (_INT, [_P, _P, _P, C.POINTER(_P)]),
     "gpl_contains_join_host": (_INT, [_P, _P, _P, _I64, _P, _I64]),
     "gpl_join_histogram": (_INT, [_P, _P, _I64, _P, _I64, _INT]),
     "gpl_gen_uniform_points": (_INT, [_P, C.c_uint64, _I64, _I64, _D, _P]),

@@ -24,7 +24,11 @@
 // These kernels are FP64-ALU bound, not HBM bound (~225 segment tests + ~480 distance items per 512 B).
 #include <math.h>
 
+#include <cmath>
+#include <string.h>
+
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace gpl {
 
@@ -773,8 +777,257 @@ __global__ void __launch_bounds__(256) k_distance_multi(int64_t n, Side a, const
     }
 }
 
+// ---- (Multi)Polygon contains Polygon (spatial_index.rs:99-110: `poly_lhs.contains(poly_rhs)`) -------------------------
+// geo 0.27 contains/polygon.rs (recalled): `impl_contains_from_relate!`, i.e. self.relate(rhs).is_contains() = DE-9IM
+// [T*****FF*].  For VALID operands: B inside closure(A) and the interiors meet, decided with exact orientation signs only
+// (the derivation is in oracle/geo_oracle.c, "Polygon / MultiPolygon contains Polygon"):
+//   C1 no edge of B leaves closure(A): just after its start and just after every A vertex lying on it the edge is not in
+//      the exterior of A, and it crosses no A edge properly (unless an A vertex sits on the crossing);
+//   C2 no edge of A enters the interior of B (same events, roles swapped);
+//   C3 a point just beside B's first edge, on B's interior side, is inside A.
+// "Just after / beside" are symbolic points q = x + eps (v - x) + eps^2 side L(v - x): every comparison of geo's
+// coord_pos_relative_to_ring is made on x first and on the eps / eps^2 terms on a tie — all exact signs.
+struct SymQ {
+    double xx, xy, vx, vy;
+    int side;
+};
+__device__ __forceinline__ int cmpd(double a, double b) { return (a > b) - (a < b); }
+__device__ __forceinline__ int sgnd(double a) { return (a > 0.0) - (a < 0.0); }
+__device__ __forceinline__ int sym_cmp_y(const SymQ &q, double cy) {  // sign of cy - q.y
+    int c = cmpd(cy, q.xy);
+    if (c) return c;
+    c = -cmpd(q.vy, q.xy);
+    if (c) return c;
+    return -q.side * cmpd(q.vx, q.xx);
+}
+__device__ __forceinline__ int sym_cmp_x(const SymQ &q, double cx) {  // sign of cx - q.x
+    int c = cmpd(cx, q.xx);
+    if (c) return c;
+    c = -cmpd(q.vx, q.xx);
+    if (c) return c;
+    return q.side * cmpd(q.vy, q.xy);
+}
+__device__ __forceinline__ int sym_orient(double2 s, double2 e, const SymQ &q) {  // sign of orient2d(s, e, q)
+    int o = sgnd(orient2d(s.x, s.y, e.x, e.y, q.xx, q.xy));
+    if (o) return o;
+    o = sgnd(orient2d(s.x, s.y, e.x, e.y, q.vx, q.vy));
+    if (o || !q.side) return o;
+    int d1, d2;  // s, e, x, v collinear: sign of side * dot(e - s, v - x)
+    if (e.x != s.x) d1 = cmpd(e.x, s.x), d2 = cmpd(q.vx, q.xx);
+    else d1 = cmpd(e.y, s.y), d2 = cmpd(q.vy, q.xy);
+    return q.side * d1 * d2;
+}
+__device__ __forceinline__ bool sym_between_x(const SymQ &q, double b1, double b2) {
+    if (b1 < b2) return sym_cmp_x(q, b1) <= 0 && sym_cmp_x(q, b2) >= 0;
+    return sym_cmp_x(q, b2) <= 0 && sym_cmp_x(q, b1) >= 0;
+}
+// 0 outside / 1 boundary / 2 inside; lanes stride over the ring's segments
+__device__ __forceinline__ int sym_ring_pos(const SymQ &q, const Chain &c, int lane) {
+    if (c.n < 2) return 0;
+    const int64_t m = c.coords();
+    int wn = 0;
+    bool boundary = false;
+    for (int64_t i = lane; i + 1 < m; i += 32) {
+        const double2 s = c[i], e = c[i + 1];
+        const int cs = sym_cmp_y(q, s.y), ce = sym_cmp_y(q, e.y);
+        if (cs <= 0) {
+            if (ce >= 0) {
+                const int o = sym_orient(s, e, q);
+                if (o > 0 && ce != 0) wn += 1;
+                else if (o == 0 && sym_between_x(q, s.x, e.x)) boundary = true;
+            }
+        } else if (ce <= 0) {
+            const int o = sym_orient(s, e, q);
+            if (o < 0) wn -= 1;
+            else if (o == 0 && sym_between_x(q, s.x, e.x)) boundary = true;
+        }
+    }
+    if (__any_sync(0xffffffffu, boundary)) return 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    return wn ? 2 : 0;
+}
+// position of q in the union of the polygon members [m0, m1) of the POLYGON view `a`
+__device__ __forceinline__ int sym_region_pos(const Side &a, int64_t m0, int64_t m1, const SymQ &q, int lane) {
+    bool boundary = false;
+    for (int64_t m = m0; m < m1; ++m) {
+        const int64_t r0 = a.go[m], r1 = a.go[m + 1];
+        if (r1 <= r0) continue;
+        const int pe = sym_ring_pos(q, part_ring(a, r0), lane);
+        if (pe == 0) continue;
+        if (pe == 1) {
+            boundary = true;
+            continue;
+        }
+        bool in_hole = false;
+        for (int64_t r = r0 + 1; r < r1 && !in_hole; ++r) {
+            const int ph = sym_ring_pos(q, part_ring(a, r), lane);
+            if (ph == 2) in_hole = true;
+            else if (ph == 1) in_hole = boundary = true;
+        }
+        if (!in_hole) return 2;
+    }
+    return boundary ? 1 : 0;
+}
+__device__ __forceinline__ bool strictly_between(double2 c, double2 u, double2 v) {
+    if (u.x != v.x) return c.x > fmin(u.x, v.x) && c.x < fmax(u.x, v.x);
+    return c.y > fmin(u.y, v.y) && c.y < fmax(u.y, v.y);
+}
+// is some vertex of the members [m0, m1) of `a` on both lines u-v and s-e (exactly at their crossing)?
+__device__ __forceinline__ bool vertex_at_crossing(const Side &a, int64_t m0, int64_t m1, double2 u, double2 v, double2 s, double2 e, int lane) {
+    bool hit = false;
+    for (int64_t c = a.ro[a.go[m0]] + lane; c < a.ro[a.go[m1]]; c += 32) {
+        const double2 w = a.xy[c];
+        hit = hit || (orient2d(u.x, u.y, v.x, v.y, w.x, w.y) == 0.0 && orient2d(s.x, s.y, e.x, e.y, w.x, w.y) == 0.0);
+    }
+    return __any_sync(0xffffffffu, hit);
+}
+__device__ __forceinline__ double2 bcast2(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+// the edges of X = members [x0,x1) of view x must not reach into `forbidden` (0 exterior / 2 interior) of Y = members
+// [y0,y1) of view y; check_cross: a proper crossing fails (C1).  Warp-uniform control flow.
+__device__ __forceinline__ bool edges_avoid(const Side &x, int64_t x0, int64_t x1, const Side &y, int64_t y0, int64_t y1, int forbidden,
+                                            bool check_cross, int lane) {
+    for (int64_t rx = x.go[x0]; rx < x.go[x1]; ++rx) {
+        const Chain cx = part_ring(x, rx);
+        const int64_t nx = cx.coords();
+        for (int64_t i = 0; i + 1 < nx; ++i) {
+            const double2 u = cx[i], v = cx[i + 1];
+            if (u.x == v.x && u.y == v.y) continue;
+            const SymQ q{u.x, u.y, v.x, v.y, 0};
+            if (sym_region_pos(y, y0, y1, q, lane) == forbidden) return false;
+            for (int64_t ry = y.go[y0]; ry < y.go[y1]; ++ry) {
+                const Chain cy = part_ring(y, ry);
+                const int64_t ny = cy.coords();
+                for (int64_t j0 = 0; j0 + 1 < ny; j0 += 32) {
+                    const int64_t j = j0 + lane;
+                    bool cross = false, touch = false;
+                    double2 s = make_double2(0.0, 0.0), e = s;
+                    if (j + 1 < ny) {
+                        s = cy[j], e = cy[j + 1];
+                        const int o1 = sgnd(orient2d(u.x, u.y, v.x, v.y, s.x, s.y));
+                        if (check_cross && !(s.x == e.x && s.y == e.y)) {
+                            const int o2 = sgnd(orient2d(u.x, u.y, v.x, v.y, e.x, e.y));
+                            if (o1 * o2 < 0) {
+                                const int o3 = sgnd(orient2d(s.x, s.y, e.x, e.y, u.x, u.y)), o4 = sgnd(orient2d(s.x, s.y, e.x, e.y, v.x, v.y));
+                                cross = o3 * o4 < 0;
+                            }
+                        }
+                        touch = o1 == 0 && strictly_between(s, u, v);
+                    }
+                    unsigned mc = __ballot_sync(0xffffffffu, cross);
+                    while (mc) {  // an A vertex exactly on the crossing (members touching there) leaves the verdict to `touch`
+                        const int src = __ffs(mc) - 1;
+                        mc &= mc - 1;
+                        if (!vertex_at_crossing(y, y0, y1, u, v, bcast2(s, src), bcast2(e, src), lane)) return false;
+                    }
+                    unsigned mt = __ballot_sync(0xffffffffu, touch);
+                    while (mt) {  // a vertex of Y inside this edge: the part of the edge after it
+                        const int src = __ffs(mt) - 1;
+                        mt &= mt - 1;
+                        const double2 w = bcast2(s, src);
+                        const SymQ q2{w.x, w.y, v.x, v.y, 0};
+                        if (sym_region_pos(y, y0, y1, q2, lane) == forbidden) return false;
+                    }
+                }
+            }
+        }
+    }
+    return true;
+}
+// A = members [a0,a1) of the POLYGON view `a`; B = polygon b of the POLYGON view `bv`
+__device__ __forceinline__ bool region_contains_polygon(const Side &a, int64_t a0, int64_t a1, const Side &bv, int64_t b, int lane) {
+    const int64_t br0 = bv.go[b], br1 = bv.go[b + 1];
+    if (a1 <= a0 || br1 <= br0 || bv.ro[br0 + 1] - bv.ro[br0] < 3) return false;
+    if (!edges_avoid(bv, b, b + 1, a, a0, a1, 0, true, lane)) return false;   // C1
+    if (!edges_avoid(a, a0, a1, bv, b, b + 1, 2, false, lane)) return false;  // C2
+    const Chain ce = part_ring(bv, br0);
+    const int64_t n = ce.coords();
+    for (int64_t i = 0; i + 1 < n; ++i) {  // C3: the first non-degenerate edge of B's exterior ring
+        const double2 u = ce[i], v = ce[i + 1];
+        if (u.x == v.x && u.y == v.y) continue;
+        SymQ q{u.x, u.y, v.x, v.y, 1};
+        if (sym_region_pos(bv, b, b + 1, q, lane) != 2) {
+            q.side = -1;
+            if (sym_region_pos(bv, b, b + 1, q, lane) != 2) return false;  // no interior beside its own boundary: degenerate
+        }
+        return sym_region_pos(a, a0, a1, q, lane) == 2;
+    }
+    return false;
+}
+// One warp per row (or per candidate pair of a join: ia / ib select the rows).  a: POLYGON view of the (Multi)Polygon
+// side, am its member offsets (NULL: one member per row); b: POLYGON.
+__global__ void __launch_bounds__(256) k_contains_polygon(int64_t n, Side a, const int64_t *__restrict__ am, const uint8_t *__restrict__ av,
+                                                          Side b, const uint8_t *__restrict__ bv, const uint64_t *__restrict__ ia,
+                                                          const uint64_t *__restrict__ ib, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t ra = ia ? (int64_t)ia[r] : r, rb = ib ? (int64_t)ib[r] : r;
+        bool res = false;
+        if (bit_get(av, ra) && bit_get(bv, rb)) {
+            const int64_t m0 = am ? am[ra] : ra, m1 = am ? am[ra + 1] : ra + 1;
+            res = region_contains_polygon(a, m0, m1, b, rb, lane);
+        }
+        if (lane == 0) out[r] = res ? 1 : 0;
+    }
+}
+// row_intersects over candidate pairs of a join
+__global__ void __launch_bounds__(256) k_intersects_pairs(int64_t n, Side a, const uint8_t *__restrict__ av, Side b,
+                                                          const uint8_t *__restrict__ bv, const uint64_t *__restrict__ ia,
+                                                          const uint64_t *__restrict__ ib, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t ra = (int64_t)ia[r], rb = (int64_t)ib[r];
+        bool res = false;
+        if (bit_get(av, ra) && bit_get(bv, rb)) res = row_intersects(a, ra, b, rb, lane);
+        if (lane == 0) out[r] = res ? 1 : 0;
+    }
+}
+
 // impl Contains<Coord> for LineString (interior only: an end point counts only on a closed linestring);
 // MultiLineString: any member.  geo 0.27 contains/line_string.rs, contains/line.rs (recalled).
+__device__ __forceinline__ bool lines_contain_point(const Side &a, int64_t r, double2 p, int lane) {
+    bool res = false;
+    int64_t k0, k1;
+    side_range(a, r, k0, k1);
+    for (int64_t k = k0; k < k1 && !res; ++k) {
+        const Chain c = side_chain(a, r, k);
+        if (c.n == 0) continue;
+        const double2 f = c.p[0], l = c.p[c.n - 1];
+        if ((p.x == f.x && p.y == f.y) || (p.x == l.x && p.y == l.y)) {
+            res = (f.x == l.x && f.y == l.y);  // is_closed()
+            continue;
+        }
+        bool hit = false;
+        for (int64_t i = lane; i + 1 < c.n; i += 32) {
+            const double2 s = c.p[i], e = c.p[i + 1];
+            const bool ps = (p.x == s.x && p.y == s.y), pe = (p.x == e.x && p.y == e.y);
+            const bool in_line = (s.x == e.x && s.y == e.y) ? ps : (!ps && !pe && line_intersects_coord(s, e, p));
+            hit = hit || in_line || (i > 0 && ps);
+        }
+        res = __any_sync(0xffffffffu, hit);
+    }
+    return res;
+}
+// (Multi)Polygon::contains(coord): strictly inside some part (geo coordinate_position == Inside)
+__device__ __forceinline__ bool area_contains_point(const Side &a, int64_t r, double2 p, int lane) {
+    int64_t q0, q1;
+    side_range(a, r, q0, q1);
+    for (int64_t q = q0; q < q1; ++q) {
+        int64_t r0, r1;
+        side_part(a, r, q, r0, r1);
+        bool inside = false;
+        int bc = 0;
+        polygon_position(a.xy, a.ro, r0, r1, p, lane, inside, bc);
+        if ((bc % 2 == 0) && inside) return true;
+    }
+    return false;
+}
 __global__ void __launch_bounds__(256) k_lines_contain_point(int64_t n, Side a, const uint8_t *__restrict__ av,
                                                              const double2 *__restrict__ pts, const uint8_t *__restrict__ pv,
                                                              uint8_t *__restrict__ out) {
@@ -783,29 +1036,27 @@ __global__ void __launch_bounds__(256) k_lines_contain_point(int64_t n, Side a, 
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
         bool res = false;
-        if (bit_get(av, r) && bit_get(pv, r)) {
-            const double2 p = pts[r];
-            int64_t k0, k1;
-            side_range(a, r, k0, k1);
-            for (int64_t k = k0; k < k1 && !res; ++k) {
-                const Chain c = side_chain(a, r, k);
-                if (c.n == 0) continue;
-                const double2 f = c.p[0], l = c.p[c.n - 1];
-                if ((p.x == f.x && p.y == f.y) || (p.x == l.x && p.y == l.y)) {
-                    res = (f.x == l.x && f.y == l.y);  // is_closed()
-                    continue;
-                }
-                bool hit = false;
-                for (int64_t i = lane; i + 1 < c.n; i += 32) {
-                    const double2 s = c.p[i], e = c.p[i + 1];
-                    const bool ps = (p.x == s.x && p.y == s.y), pe = (p.x == e.x && p.y == e.y);
-                    const bool in_line = (s.x == e.x && s.y == e.y) ? ps : (!ps && !pe && line_intersects_coord(s, e, p));
-                    hit = hit || in_line || (i > 0 && ps);
-                }
-                res = __any_sync(0xffffffffu, hit);
-            }
-        }
+        if (bit_get(av, r) && bit_get(pv, r)) res = lines_contain_point(a, r, pts[r], lane);
         if (lane == 0) out[r] = res ? 1 : 0;
+    }
+}
+// candidate pairs of a join: row ia[k] of the (Multi)Polygon / (Multi)LineString side contains point row ib[k]
+__global__ void __launch_bounds__(256) k_contains_point_pairs(int64_t n, Side a, const uint8_t *__restrict__ av,
+                                                              const double2 *__restrict__ pts, const uint8_t *__restrict__ pv,
+                                                              const uint64_t *__restrict__ ia, const uint64_t *__restrict__ ib,
+                                                              uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool lines = side_class(a.type) == 1;
+    for (int64_t k = warp; k < n; k += nwarps) {
+        const int64_t ra = (int64_t)ia[k], rb = (int64_t)ib[k];
+        bool res = false;
+        if (bit_get(av, ra) && bit_get(pv, rb)) {
+            const double2 p = pts[rb];
+            res = lines ? lines_contain_point(a, ra, p, lane) : area_contains_point(a, ra, p, lane);
+        }
+        if (lane == 0) out[k] = res ? 1 : 0;
     }
 }
 
@@ -907,6 +1158,7 @@ static int warp_grid(int64_t rows, int warps_per_cta) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * 16));
 }
 
+static int side_class_host(int t) { return (t == GPL_POINT || t == GPL_MULTIPOINT) ? 0 : (t == GPL_LINESTRING || t == GPL_MULTILINESTRING) ? 1 : 2; }
 static const char *type_name(int t) {
     switch (t) {
     case GPL_POINT: return "Point";
@@ -1047,4 +1299,265 @@ extern "C" int gpl_distance(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b
     }
     if (out_validity) GPL_TRY(finish_bitmap(ctx, vb, n, out_validity, mem));
     return deliver(ctx, out, dst, sizeof(double) * n, mem);
+}
+
+// ================================================================================================================
+// general spatial join: spatial_join(lhs, rhs, predicate) for any two geometry columns (spatial_index.rs:37-157)
+// ================================================================================================================
+// Reference: both sides get an R-tree of per-row envelopes (:314-350), `intersection_candidates_with_other_tree`
+// yields every pair whose envelopes intersect (closed intervals, :74-76), and each pair is tested by type-pair dispatch
+// (:89-137); pairs that pass are emitted as (lhs_index, rhs_index) in tree-traversal order (unspecified; compare as sets).
+// Here: envelopes of both sides (k_envelope), a uniform grid over the union box of the RIGHT envelopes holding, per cell,
+// the rows whose envelope overlaps it; one thread per LEFT row walks the cells its envelope overlaps and keeps the
+// candidates whose envelope intersects (each pair is reported from the single cell that holds the lower-left corner of
+// the intersection box); count -> scan -> write gives the candidate list, a warp per candidate evaluates the
+// dispatched predicate, and a second scan compacts the hits.  Points x (Multi)Polygons with millions of points should
+// use gpl_pip_index_build + gpl_contains_join (the north-star path); this entry point is the general one.
+struct gpl_pairs {  // also defined (identically) in k_pip.cu for gpl_contains_join_pairs_array
+    gpl_ctx *ctx = nullptr;
+    uint64_t *lhs = nullptr, *rhs = nullptr;  // device
+    int64_t n = 0;
+};
+
+namespace gpl {
+
+int envelope_raw(gpl_ctx *ctx, const gpl_array *in, double *out4_dev, uint8_t *valid_bytes_dev);
+
+struct JoinGrid {
+    double x0, y0, inv_w, inv_h;
+    int32_t g;
+};
+__device__ __forceinline__ int32_t jg_cell(double v, double lo, double inv, int32_t g) {
+    return min(max(__double2int_rd((v - lo) * inv), 0), g - 1);  // monotone (see k_pip.cu fine_index)
+}
+// union box of the valid envelopes: block reduce + ordered atomics (acc[0..3] zeroed by the host)
+__global__ void __launch_bounds__(256) k_join_union(const double *__restrict__ b4, const uint8_t *__restrict__ has, int64_t n,
+                                                    unsigned long long *__restrict__ acc) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double x0 = inf, y0 = inf, x1 = -inf, y1 = -inf;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (has[i]) x0 = fmin(x0, b4[4 * i]), y0 = fmin(y0, b4[4 * i + 1]), x1 = fmax(x1, b4[4 * i + 2]), y1 = fmax(y1, b4[4 * i + 3]);
+    x0 = warp_min(x0), y0 = warp_min(y0), x1 = warp_max(x1), y1 = warp_max(y1);
+    auto enc = [](double d) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+    };
+    if ((threadIdx.x & 31) == 0 && x0 <= x1 && y0 <= y1) {
+        atomicMax(acc + 0, ~enc(x0));
+        atomicMax(acc + 1, ~enc(y0));
+        atomicMax(acc + 2, enc(x1));
+        atomicMax(acc + 3, enc(y1));
+    }
+}
+// right rows into grid cells: pass 0 counts, pass 1 fills
+template <int PASS>
+__global__ void k_join_cells(const double *__restrict__ b4, const uint8_t *__restrict__ has, int64_t n, JoinGrid jg,
+                             int32_t *__restrict__ count_or_cursor, int32_t *__restrict__ items) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !has[i]) return;
+    const int32_t cx0 = jg_cell(b4[4 * i], jg.x0, jg.inv_w, jg.g), cx1 = jg_cell(b4[4 * i + 2], jg.x0, jg.inv_w, jg.g);
+    const int32_t cy0 = jg_cell(b4[4 * i + 1], jg.y0, jg.inv_h, jg.g), cy1 = jg_cell(b4[4 * i + 3], jg.y0, jg.inv_h, jg.g);
+    for (int32_t cy = cy0; cy <= cy1; ++cy)
+        for (int32_t cx = cx0; cx <= cx1; ++cx) {
+            const int64_t c = (int64_t)cy * jg.g + cx;
+            if (PASS == 0) atomicAdd(&count_or_cursor[c], 1);
+            else items[atomicAdd(&count_or_cursor[c], 1)] = (int32_t)i;
+        }
+}
+// candidates of each left row: pass 0 counts, pass 1 writes (lhs, rhs) at off[i]
+template <int PASS>
+__global__ void k_join_candidates(const double *__restrict__ l4, const uint8_t *__restrict__ lhas, int64_t nl, const double *__restrict__ r4,
+                                  JoinGrid jg, double ux1, double uy1, const int32_t *__restrict__ cell_start,
+                                  const int32_t *__restrict__ items, int32_t *__restrict__ counts, const int64_t *__restrict__ off,
+                                  uint64_t *__restrict__ lhs, uint64_t *__restrict__ rhs) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    int32_t cnt = 0;
+    int64_t w = PASS == 1 ? off[i] : 0;
+    if (lhas[i]) {
+        const double lx0 = l4[4 * i], ly0 = l4[4 * i + 1], lx1 = l4[4 * i + 2], ly1 = l4[4 * i + 3];
+        // outside the union box of the right side: no candidate (closed intervals)
+        if (!(lx1 < jg.x0 || ly1 < jg.y0 || lx0 > ux1 || ly0 > uy1)) {
+            const int32_t cx0 = jg_cell(lx0, jg.x0, jg.inv_w, jg.g), cx1 = jg_cell(lx1, jg.x0, jg.inv_w, jg.g);
+            const int32_t cy0 = jg_cell(ly0, jg.y0, jg.inv_h, jg.g), cy1 = jg_cell(ly1, jg.y0, jg.inv_h, jg.g);
+            for (int32_t cy = cy0; cy <= cy1; ++cy)
+                for (int32_t cx = cx0; cx <= cx1; ++cx) {
+                    const int64_t c = (int64_t)cy * jg.g + cx;
+                    for (int32_t k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                        const int32_t j = items[k];
+                        const double rx0 = r4[4 * j], ry0 = r4[4 * j + 1], rx1 = r4[4 * j + 2], ry1 = r4[4 * j + 3];
+                        if (lx0 > rx1 || rx0 > lx1 || ly0 > ry1 || ry0 > ly1) continue;  // AABB intersection, closed
+                        // report the pair from the one cell that holds the lower-left corner of the intersection box
+                        if (jg_cell(fmax(lx0, rx0), jg.x0, jg.inv_w, jg.g) != cx || jg_cell(fmax(ly0, ry0), jg.y0, jg.inv_h, jg.g) != cy) continue;
+                        if (PASS == 1) lhs[w] = (uint64_t)i, rhs[w] = (uint64_t)j, ++w;
+                        ++cnt;
+                    }
+                }
+        }
+    }
+    if (PASS == 0) counts[i] = cnt;
+}
+__global__ void k_join_compact(const uint8_t *__restrict__ hit, const int64_t *__restrict__ off, int64_t n, const uint64_t *__restrict__ cl,
+                               const uint64_t *__restrict__ cr, uint64_t *__restrict__ ol, uint64_t *__restrict__ orr) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n && hit[k]) ol[off[k]] = cl[k], orr[off[k]] = cr[k];
+}
+
+static Side polygon_view(const gpl_array *g) {
+    const double2 *xy = reinterpret_cast<const double2 *>(g->xy);
+    if (g->type == GPL_MULTIPOLYGON) return Side{GPL_POLYGON, xy, g->part_off, nullptr, g->ring_off};
+    return Side{g->type, xy, g->geom_off, g->part_off, g->ring_off};
+}
+
+}  // namespace gpl
+
+extern "C" void gpl_pairs_free(gpl_pairs *p) {
+    if (!p) return;
+    p->ctx->release(p->lhs);
+    p->ctx->release(p->rhs);
+    delete p;
+}
+extern "C" int64_t gpl_pairs_count(const gpl_pairs *p) { return p ? p->n : 0; }
+extern "C" int gpl_pairs_copy(gpl_ctx *ctx, const gpl_pairs *p, uint64_t *lhs, uint64_t *rhs, int mem) {
+    GPL_REQUIRE(ctx && p && (p->n == 0 || (lhs && rhs)), GPL_ERR_INVALID_ARG, "gpl_pairs_copy: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    if (p->n == 0) return GPL_OK;
+    const cudaMemcpyKind kind = mem == GPL_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    GPL_CUDA(cudaMemcpyAsync(lhs, p->lhs, sizeof(uint64_t) * p->n, kind, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(rhs, p->rhs, sizeof(uint64_t) * p->n, kind, ctx->stream));
+    if (mem == GPL_HOST) GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPL_OK;
+}
+
+// row-wise (Multi)Polygon.contains(Polygon)
+extern "C" int gpl_contains_polygon(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, uint8_t *out_bitmap, int mem) {
+    GPL_REQUIRE(ctx && a && b && out_bitmap, GPL_ERR_INVALID_ARG, "gpl_contains_polygon: NULL argument");
+    GPL_REQUIRE(a->n_geoms == b->n_geoms, GPL_ERR_LENGTH_MISMATCH, "contains: lengths differ (%lld vs %lld)", (long long)a->n_geoms,
+                (long long)b->n_geoms);
+    GPL_REQUIRE((a->type == GPL_POLYGON || a->type == GPL_MULTIPOLYGON) && b->type == GPL_POLYGON, GPL_ERR_INVALID_TYPE,
+                "Expected (Multi)Polygon x Polygon (found %s x %s)", type_name(a->type), type_name(b->type));
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = a->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<uint8_t> bytes;
+    GPL_TRY(bytes.get(ctx, (size_t)n));
+    GPL_LAUNCH(ctx, k_contains_polygon, warp_grid(n, 8), 256, 0, n, polygon_view(a), a->type == GPL_MULTIPOLYGON ? a->geom_off : nullptr, a->validity,
+               polygon_view(b), b->validity, nullptr, nullptr, bytes.p);
+    return finish_bitmap(ctx, bytes.p, n, out_bitmap, mem);
+}
+
+extern "C" int gpl_spatial_join(gpl_ctx *ctx, const gpl_array *lhs, const gpl_array *rhs, int predicate, gpl_pairs **out) {
+    GPL_REQUIRE(ctx && lhs && rhs && out, GPL_ERR_INVALID_ARG, "gpl_spatial_join: NULL argument");
+    GPL_REQUIRE(predicate == GPL_PREDICATE_INTERSECTS || predicate == GPL_PREDICATE_CONTAINS, GPL_ERR_INVALID_ARG,
+                "gpl_spatial_join: predicate must be GPL_PREDICATE_INTERSECTS or GPL_PREDICATE_CONTAINS");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    gpl_pairs *res = new gpl_pairs();
+    res->ctx = ctx;
+    *out = res;
+    const int64_t nl = lhs->n_geoms, nr = rhs->n_geoms;
+    if (nl == 0 || nr == 0) return GPL_OK;
+    GPL_REQUIRE(nl < (1LL << 31) && nr < (1LL << 31), GPL_ERR_UNSUPPORTED, "gpl_spatial_join: at most 2^31 rows per side");
+    // ---- the type-pair dispatch table of spatial_index.rs:89-137 (anything else: no pair matches) ------------------------
+    const int tl = lhs->type, tr = rhs->type;
+    const int cl_ = side_class_host(tl), cr_ = side_class_host(tr);
+    enum { NONE, POINT_IN_R, POINT_IN_L, POLY_CONTAINS, INTERSECTS } mode = NONE;
+    if (tl == GPL_POINT && (cr_ == 2 || tr == GPL_LINESTRING || tr == GPL_MULTILINESTRING)) mode = POINT_IN_R;       // :91, :95, :130-134
+    else if (tr == GPL_POINT && (cl_ == 2 || tl == GPL_LINESTRING || tl == GPL_MULTILINESTRING)) mode = POINT_IN_L;  // :92, :96, :129-133
+    else if ((tl == GPL_POLYGON || tl == GPL_MULTIPOLYGON) && tr == GPL_POLYGON) mode = predicate == GPL_PREDICATE_CONTAINS ? POLY_CONTAINS : INTERSECTS;  // :99-115
+    else if (tl == GPL_POLYGON && tr == GPL_MULTIPOLYGON && predicate == GPL_PREDICATE_INTERSECTS) mode = INTERSECTS;  // :118-122
+    if (mode == NONE) return GPL_OK;
+    // ---- envelopes -----------------------------------------------------------------------------------------------------
+    Scratch<double> l4, r4;
+    Scratch<uint8_t> lh, rh;
+    GPL_TRY(l4.get(ctx, (size_t)nl * 4));
+    GPL_TRY(r4.get(ctx, (size_t)nr * 4));
+    GPL_TRY(lh.get(ctx, (size_t)nl));
+    GPL_TRY(rh.get(ctx, (size_t)nr));
+    GPL_TRY(envelope_raw(ctx, lhs, l4.p, lh.p));
+    GPL_TRY(envelope_raw(ctx, rhs, r4.p, rh.p));
+    // ---- grid over the right side's union box ------------------------------------------------------------------------------
+    Scratch<unsigned long long> acc;
+    GPL_TRY(acc.get(ctx, 4));
+    GPL_CUDA(cudaMemsetAsync(acc.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    GPL_LAUNCH(ctx, k_join_union, (int)std::min<int64_t>(ceil_div(nr, 256), kSMs * 8), 256, 0, r4.p, rh.p, nr, acc.p);
+    unsigned long long h_acc[4];
+    GPL_CUDA(cudaMemcpyAsync(h_acc, acc.p, sizeof(h_acc), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_acc[2] == 0ULL) return GPL_OK;  // no right row has an envelope
+    auto dec = [](unsigned long long u) {
+        const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+        double d;
+        memcpy(&d, &b, sizeof(d));
+        return d;
+    };
+    const double ux0 = dec(~h_acc[0]), uy0 = dec(~h_acc[1]), ux1 = dec(h_acc[2]), uy1 = dec(h_acc[3]);
+    JoinGrid jg;
+    jg.g = (int32_t)std::min<int64_t>(2048, std::max<int64_t>(1, (int64_t)ceil(sqrt((double)nr))));
+    jg.x0 = ux0, jg.y0 = uy0;
+    const double w = ux1 - ux0, h = uy1 - uy0;
+    jg.inv_w = (w > 0.0 && std::isfinite(w) && std::isfinite(jg.g / w)) ? jg.g / w : 0.0;
+    jg.inv_h = (h > 0.0 && std::isfinite(h) && std::isfinite(jg.g / h)) ? jg.g / h : 0.0;
+    const int64_t n_cells = (int64_t)jg.g * jg.g;
+    Scratch<int32_t> cell_count, cell_start, items, cand_count;
+    Scratch<int64_t> tot, cand_off;
+    GPL_TRY(cell_count.get(ctx, (size_t)n_cells + 1));
+    GPL_TRY(cell_start.get(ctx, (size_t)n_cells + 1));
+    GPL_TRY(tot.get(ctx, 2));
+    GPL_CUDA(cudaMemsetAsync(cell_count.p, 0, sizeof(int32_t) * (n_cells + 1), ctx->stream));
+    GPL_LAUNCH(ctx, k_join_cells<0>, (int)ceil_div(nr, 128), 128, 0, r4.p, rh.p, nr, jg, cell_count.p, nullptr);
+    GPL_TRY((exclusive_scan<int32_t, int32_t>(ctx, cell_count.p, n_cells, cell_start.p, tot.p)));
+    int64_t n_items = 0;
+    GPL_CUDA(cudaMemcpyAsync(&n_items, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    GPL_REQUIRE(n_items < (1LL << 31), GPL_ERR_UNSUPPORTED, "gpl_spatial_join: grid too dense (%lld cell items)", (long long)n_items);
+    GPL_TRY(items.get(ctx, (size_t)n_items + 1));
+    GPL_CUDA(cudaMemcpyAsync(cell_count.p, cell_start.p, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToDevice, ctx->stream));  // cursors
+    GPL_LAUNCH(ctx, k_join_cells<1>, (int)ceil_div(nr, 128), 128, 0, r4.p, rh.p, nr, jg, cell_count.p, items.p);
+    // ---- candidates: count -> scan -> write ----------------------------------------------------------------------------------
+    GPL_TRY(cand_count.get(ctx, (size_t)nl + 1));
+    GPL_TRY(cand_off.get(ctx, (size_t)nl + 2));
+    GPL_LAUNCH(ctx, k_join_candidates<0>, (int)ceil_div(nl, 128), 128, 0, l4.p, lh.p, nl, r4.p, jg, ux1, uy1, cell_start.p, items.p, cand_count.p,
+               nullptr, nullptr, nullptr);
+    GPL_TRY((exclusive_scan<int32_t, int64_t>(ctx, cand_count.p, nl, cand_off.p, tot.p + 1)));
+    int64_t n_cand = 0;
+    GPL_CUDA(cudaMemcpyAsync(&n_cand, tot.p + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_cand == 0) return GPL_OK;
+    Scratch<uint64_t> cl, cr;
+    GPL_TRY(cl.get(ctx, (size_t)n_cand));
+    GPL_TRY(cr.get(ctx, (size_t)n_cand));
+    GPL_LAUNCH(ctx, k_join_candidates<1>, (int)ceil_div(nl, 128), 128, 0, l4.p, lh.p, nl, r4.p, jg, ux1, uy1, cell_start.p, items.p, nullptr,
+               cand_off.p, cl.p, cr.p);
+    // ---- exact predicate per candidate ------------------------------------------------------------------------------------------
+    Scratch<uint8_t> hit;
+    GPL_TRY(hit.get(ctx, (size_t)n_cand));
+    const double2 *lxy = reinterpret_cast<const double2 *>(lhs->xy), *rxy = reinterpret_cast<const double2 *>(rhs->xy);
+    const Side sl{tl, lxy, lhs->geom_off, lhs->part_off, lhs->ring_off}, sr{tr, rxy, rhs->geom_off, rhs->part_off, rhs->ring_off};
+    const int pgrid = warp_grid(n_cand, 8);
+    switch (mode) {
+    case POINT_IN_R: GPL_LAUNCH(ctx, k_contains_point_pairs, pgrid, 256, 0, n_cand, sr, rhs->validity, lxy, lhs->validity, cr.p, cl.p, hit.p); break;
+    case POINT_IN_L: GPL_LAUNCH(ctx, k_contains_point_pairs, pgrid, 256, 0, n_cand, sl, lhs->validity, rxy, rhs->validity, cl.p, cr.p, hit.p); break;
+    case POLY_CONTAINS:
+        GPL_LAUNCH(ctx, k_contains_polygon, pgrid, 256, 0, n_cand, polygon_view(lhs), tl == GPL_MULTIPOLYGON ? lhs->geom_off : nullptr, lhs->validity,
+                   polygon_view(rhs), rhs->validity, cl.p, cr.p, hit.p);
+        break;
+    default: GPL_LAUNCH(ctx, k_intersects_pairs, pgrid, 256, 0, n_cand, sl, lhs->validity, sr, rhs->validity, cl.p, cr.p, hit.p); break;
+    }
+    // ---- compaction ----------------------------------------------------------------------------------------------------------------
+    Scratch<int64_t> hit_off;
+    GPL_TRY(hit_off.get(ctx, (size_t)n_cand + 2));
+    GPL_TRY((exclusive_scan<uint8_t, int64_t>(ctx, hit.p, n_cand, hit_off.p, tot.p)));
+    int64_t n_hit = 0;
+    GPL_CUDA(cudaMemcpyAsync(&n_hit, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_hit == 0) return GPL_OK;
+    void *pl = nullptr, *pr = nullptr;
+    GPL_TRY(ctx->alloc(sizeof(uint64_t) * (size_t)n_hit, &pl));
+    res->lhs = (uint64_t *)pl;
+    GPL_TRY(ctx->alloc(sizeof(uint64_t) * (size_t)n_hit, &pr));
+    res->rhs = (uint64_t *)pr;
+    res->n = n_hit;
+    GPL_LAUNCH(ctx, k_join_compact, (int)ceil_div(n_cand, 256), 256, 0, hit.p, hit_off.p, n_cand, cl.p, cr.p, res->lhs, res->rhs);
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));  // the scratch lists above return to the cache when this scope ends
+    return GPL_OK;
 }

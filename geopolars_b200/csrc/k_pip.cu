@@ -209,6 +209,8 @@ struct BuildArgs {
     int32_t *bcount;        // NB_cap + 1
     int2 *side_count;       // NB_cap + 1
     int32_t *fast_c, *fast_slots;  // P + 1
+    int32_t *bucket_part;   // NB_cap + 1: the part that owns each y-bucket
+    int2 *ovf_off;          // NB_cap + 1: first overflow record of the bucket's two FP32 lists, relative to the part's base
     unsigned long long *acc;
     GridParams *gp;
     // phase 2
@@ -545,12 +547,16 @@ __device__ void ph_fast_plan(const BuildArgs &a) {
     for (int64_t p = tid; p < a.P; p += nth) {
         const PartHeader h = a.hdr[p];
         int32_t c = 0, slots = 0;
+        for (int32_t b = 0; b < h.n_buckets; ++b) a.bucket_part[h.bucket_base + b] = (int32_t)p;
         if (a.type == GPL_POLYGON && (h.flags & 2) && !(h.flags & 1)) {
             int32_t mx = 0, ovf = 0;
+            const int32_t ovf0 = h.n_buckets * 2 * kFastListRecs;  // the overflow area follows the fixed-stride lists
             for (int32_t b = 0; b < h.n_buckets; ++b) {
                 mx = max(mx, a.bcount[h.bucket_base + b]);
                 const int2 sc = a.side_count[h.bucket_base + b];
-                ovf += ((max(sc.x - (kFastListRecs - 1), 0) + 1) & ~1) + ((max(sc.y - (kFastListRecs - 1), 0) + 1) & ~1);
+                const int32_t o0 = (max(sc.x - (kFastListRecs - 1), 0) + 1) & ~1, o1 = (max(sc.y - (kFastListRecs - 1), 0) + 1) & ~1;
+                a.ovf_off[h.bucket_base + b] = make_int2(ovf0 + ovf, ovf0 + ovf + o0);
+                ovf += o0 + o1;
             }
             // The filter's bounds eta = 2^-20 R and B ~ 2^-16 R^2 are formed in FLOAT: they must neither underflow
             // (R^2 subnormal: the relative-error argument of fast_edge_rule no longer holds) nor overflow (B = inf
@@ -578,54 +584,98 @@ __device__ void ph_fast_plan(const BuildArgs &a) {
         if (not_fast) atomicAdd(a.acc + ACC_NOT_FAST, not_fast);
     }
 }
-// one warp per part: both lists of every bucket (header, float edges, sentinels) and the overflow area.
-// fast_base[] = a.fast_slots scanned in place.
-__device__ void ph_fast_fill(const BuildArgs &a, const int32_t *__restrict__ bstart) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
+// One THREAD per y-bucket finishes it: sorts the bucket's edge ids (ascending => grouped by ring, deterministic),
+// materialises the 32-byte f64 records (+ ring index when holes exist) and writes the bucket's two FP32 lists (header, float
+// edges relative to the part origin, sentinels, overflow records).  Round 2's first build did these as three warp-per-part
+// phases separated by grid barriers; a part's ~22 buckets then cost ~44 dependent L2 round trips per warp.  Here every
+// load of a bucket (edge ids, coordinates) is independent of the others and 227 k buckets run side by side.
+__device__ void ph_bucket_finish(const BuildArgs &a, const int32_t *__restrict__ bstart) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     const float inf = __int_as_float(0x7f800000);
     const float4 sentinel = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
-    for (int64_t p = warp; p < a.P; p += nwarps) {
-        if (a.fast_c[p] == 0) continue;
+    constexpr int kLocal = 32;
+    for (int64_t gb = tid; gb < a.n_buckets; gb += nth) {
+        const int32_t e0 = bstart[gb], n = bstart[gb + 1] - e0;
+        const int32_t p = a.bucket_part[gb];
         const PartHeader h = a.hdr[p];
-        const double ox = (double)__double2float_rd(h.xmin), mx = (double)__double2float_ru(h.xmax), oy = h.by0;
-        const double xm = fast_split_x(h);  // == 0.5 * (ox + mx); the query kernel forms it from PartLite
-        float4 *base = a.fast + (int64_t)a.fast_slots[p];
-        int32_t ovf = h.n_buckets * 2 * kFastListRecs;  // next free overflow record (relative to base, always even)
-        for (int32_t b = 0; b < h.n_buckets; ++b) {
-            const int32_t e0 = bstart[h.bucket_base + b], n = bstart[h.bucket_base + b + 1] - e0;
-            for (int side = 0; side < 2; ++side) {
-                float4 *list = base + ((int64_t)b * 2 + side) * kFastListRecs;
-                int32_t cnt = 0;
-                for (int32_t c0 = 0; c0 < n; c0 += 32) {
-                    const int32_t j = c0 + lane;
-                    bool sel = false;
-                    EdgeRec ed{0.0, 0.0, 0.0, 0.0};
-                    if (j < n) {
-                        ed = a.entries[e0 + j];
-                        sel = side == 0 ? fmax(ed.sx, ed.ex) >= xm : fmin(ed.sx, ed.ex) <= xm;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, sel);
-                    if (sel) {
-                        const int32_t rank = cnt + __popc(m & ((1u << lane) - 1u));
-                        const float4 r = side == 0 ? make_float4(__double2float_rn(ed.sx - ox), __double2float_rn(ed.sy - oy),
-                                                                 __double2float_rn(ed.ex - ox), __double2float_rn(ed.ey - oy))
-                                                   : make_float4(__double2float_rn(mx - ed.sx), __double2float_rn(ed.sy - oy),
-                                                                 __double2float_rn(mx - ed.ex), __double2float_rn(ed.ey - oy));
-                        if (rank < kFastListRecs - 1) list[1 + rank] = r;
-                        else base[ovf + rank - (kFastListRecs - 1)] = r;
-                    }
-                    cnt += __popc(m);
+        int64_t r0, r1;
+        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
+        // ---- sort the edge ids
+        int64_t loc[kLocal];
+        const bool local = n <= kLocal;
+        if (local) {
+            for (int32_t i = 0; i < n; ++i) loc[i] = a.entry_edge[e0 + i];
+            for (int32_t i = 1; i < n; ++i) {
+                const int64_t v = loc[i];
+                int32_t j = i - 1;
+                while (j >= 0 && loc[j] > v) {
+                    loc[j + 1] = loc[j];
+                    --j;
                 }
-                const int32_t novf = max(cnt - (kFastListRecs - 1), 0), novf2 = (novf + 1) & ~1;
-                if (lane < kFastListRecs - 1 && lane >= cnt) list[1 + lane] = sentinel;
-                if (lane == 0) {
-                    list[0] = make_float4(__int_as_float(cnt), __int_as_float(novf ? ovf : 0), 0.0f, 0.0f);
-                    if (novf2 > novf) base[ovf + novf] = sentinel;
-                }
-                ovf += novf2;
+                loc[j + 1] = v;
             }
+        } else {
+            int64_t *g = a.entry_edge + e0;
+            for (int32_t i = 1; i < n; ++i) {
+                const int64_t v = g[i];
+                int32_t j = i - 1;
+                while (j >= 0 && g[j] > v) {
+                    g[j + 1] = g[j];
+                    --j;
+                }
+                g[j + 1] = v;
+            }
+        }
+        // ---- FP32 lists of this bucket (plain parts only)
+        const bool fast = a.fast_c[p] > 0;
+        const int32_t b = (int32_t)(gb - h.bucket_base);
+        float4 *base = nullptr, *list0 = nullptr, *list1 = nullptr;
+        int2 ovf = make_int2(0, 0);
+        double ox = 0.0, mx = 0.0, oy = 0.0, xm = 0.0;
+        if (fast) {
+            base = a.fast + (int64_t)a.fast_slots[p];
+            list0 = base + ((int64_t)b * 2) * kFastListRecs, list1 = list0 + kFastListRecs;
+            ovf = a.ovf_off[gb];
+            ox = (double)__double2float_rd(h.xmin), mx = (double)__double2float_ru(h.xmax), oy = h.by0;
+            xm = fast_split_x(h);  // == 0.5 * (ox + mx); the query kernel forms it from PartLite
+        }
+        int32_t c0 = 0, c1 = 0;  // lengths of the two one-sided lists
+        for (int32_t k = 0; k < n; ++k) {
+            const int64_t c = local ? loc[k] : a.entry_edge[e0 + k];
+            // ring of coordinate c: rings of a part are few; linear search from the exterior
+            int64_t r = r0;
+            while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
+            double2 s, e;
+            edge_of_slot(a.xy, c, a.ring_off[r], a.ring_off[r + 1], s, e);
+            EdgeRec rec;
+            rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
+            a.entries[e0 + k] = rec;
+            if (a.entry_ring) a.entry_ring[e0 + k] = (int32_t)(r - r0);
+            if (fast) {
+                if (fmax(s.x, e.x) >= xm) {  // right-hand list: coordinates relative to (xminf, yminf)
+                    const float4 f = make_float4(__double2float_rn(s.x - ox), __double2float_rn(s.y - oy), __double2float_rn(e.x - ox),
+                                                 __double2float_rn(e.y - oy));
+                    if (c0 < kFastListRecs - 1) list0[1 + c0] = f;
+                    else base[ovf.x + c0 - (kFastListRecs - 1)] = f;
+                    ++c0;
+                }
+                if (fmin(s.x, e.x) <= xm) {  // left-hand list, mirrored in x
+                    const float4 f = make_float4(__double2float_rn(mx - s.x), __double2float_rn(s.y - oy), __double2float_rn(mx - e.x),
+                                                 __double2float_rn(e.y - oy));
+                    if (c1 < kFastListRecs - 1) list1[1 + c1] = f;
+                    else base[ovf.y + c1 - (kFastListRecs - 1)] = f;
+                    ++c1;
+                }
+            }
+        }
+        if (fast) {
+            for (int32_t k = c0; k < kFastListRecs - 1; ++k) list0[1 + k] = sentinel;
+            for (int32_t k = c1; k < kFastListRecs - 1; ++k) list1[1 + k] = sentinel;
+            const int32_t n0 = max(c0 - (kFastListRecs - 1), 0), n1 = max(c1 - (kFastListRecs - 1), 0);
+            list0[0] = make_float4(__int_as_float(c0), __int_as_float(n0 ? ovf.x : 0), 0.0f, 0.0f);
+            list1[0] = make_float4(__int_as_float(c1), __int_as_float(n1 ? ovf.y : 0), 0.0f, 0.0f);
+            if (n0 & 1) base[ovf.x + n0] = sentinel;  // overflow runs are padded to an even number of records
+            if (n1 & 1) base[ovf.y + n1] = sentinel;
         }
     }
 }
@@ -690,33 +740,6 @@ __device__ void ph_part_recs(const BuildArgs &a) {
         a.parts[p] = r;
     }
 }
-// materialise sorted edge ids into 32-byte records (+ ring index within the part when holes exist): one warp per
-// part, lanes over the part's entries
-__device__ void ph_materialise(const BuildArgs &a, const int32_t *__restrict__ bstart) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * kBuildThreads + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * kBuildThreads) >> 5;
-    for (int64_t p = warp; p < a.P; p += nwarps) {
-        const PartHeader h = a.hdr[p];
-        if (!(h.flags & 2)) continue;
-        int64_t r0, r1;
-        part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
-        const int32_t e0 = bstart[h.bucket_base], e1 = bstart[h.bucket_base + h.n_buckets];
-        for (int32_t k = e0 + lane; k < e1; k += 32) {
-            const int64_t c = a.entry_edge[k];
-            // ring of coordinate c: rings of a part are few; linear search from the exterior
-            int64_t r = r0;
-            while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
-            double2 s, e;
-            edge_of_slot(a.xy, c, a.ring_off[r], a.ring_off[r + 1], s, e);
-            EdgeRec rec;
-            rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
-            a.entries[k] = rec;
-            if (a.entry_ring) a.entry_ring[k] = (int32_t)(r - r0);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // exact rule (shared by the raster classification, the deferred kernel and the pair mode)
 // ------------------------------------------------------------------------------------------------
@@ -859,7 +882,7 @@ __device__ __forceinline__ void raster_fill_span(const BuildArgs &a, const GridP
 // cell is outside that run, hence on the same side of both: comparing CELL indices orders the centre and the crossing
 // exactly.  Everything the lists cannot hold (more than kRowCross crossings in a row, a row whose centre does not map
 // back to it) is coded 3 over the part's whole column range, which is always safe.
-constexpr int kRowCross = 8;
+constexpr int kRowCross = 24;  // a horizontal line through a config-2 star crosses 12-17 edges
 constexpr int kRowStride = kRowCross + 1;  // odd stride: the 32 lists of a chunk do not collide on banks
 struct RasterSmem {
     int32_t cnt[kBuildThreads / 32][32];
@@ -1060,19 +1083,15 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
     ph_cells<1>(a, g);
     ph_buckets<1>(a, nullptr, 1);
     grid.sync();
-    // T3: deterministic order
+    // T3: candidate lists in ascending order; every y-bucket finished by one thread (sort, f64 records, FP32 lists)
     ph_sort_segments<int32_t>(a.items, cell_start, a.n_cells);
-    ph_sort_segments<int64_t>(a.entry_edge, bstart, a.n_buckets);
-    grid.sync();
-    // T4: records
-    ph_cell_finish(a, cell_start);
+    ph_bucket_finish(a, bstart);
     ph_part_recs(a);
     for (int64_t b = tid; b < a.n_buckets; b += nth) a.bucket_range[b] = make_int2(bstart[b], bstart[b + 1]);
-    ph_materialise(a, bstart);
-    ph_raster(a, g, cell_start, sm_raster);
     grid.sync();
-    // T5: FP32 lists
-    ph_fast_fill(a, bstart);
+    // T4: cell records (need the sorted lists), raster
+    ph_cell_finish(a, cell_start);
+    ph_raster(a, g, cell_start, sm_raster);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1463,8 +1482,10 @@ __device__ __forceinline__ void ld256s(const double2 *p, double2 &a, double2 &b)
 }
 // HIST: per-polygon hit counts (config 4's all-reduce input) in the same pass: 32-bit bins privatised per CTA in shared
 // memory behind the queues, flushed with one 64-bit global atomic per non-zero bin when the CTA retires.
-template <bool LEAN, bool HIST, int MINB>
-__global__ void __launch_bounds__(kQueryThreads, MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
+// CSM: the rows of candidate #0 of every coarse cell (raster code 1: 36 % of config 2's points) staged in shared memory —
+// the 8-byte gather from the L1-resident table cost L1/TEX tag wavefronts, the limiter of this kernel (ncu: l1tex 84 %).
+template <bool LEAN, bool HIST, bool CSM>
+__global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stream(const IndexView ix, const double2 *__restrict__ pts,
                                                                                   const uint8_t *__restrict__ pts_validity, int64_t n_pts,
                                                                                   int32_t *__restrict__ first_id, int32_t *__restrict__ count,
                                                                                   unsigned long long *__restrict__ n_deferred,
@@ -1473,8 +1494,14 @@ __global__ void __launch_bounds__(kQueryThreads, MINB) k_pip_stream(const IndexV
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
     unsigned int *bins = reinterpret_cast<unsigned int *>(smem_raw + sizeof(StreamSmem));
+    int32_t *cand0 = reinterpret_cast<int32_t *>(smem_raw + sizeof(StreamSmem));  // HIST and CSM are never combined
     if (HIST) {
         for (int32_t b = threadIdx.x; b < n_bins; b += kQueryThreads) bins[b] = 0u;
+        __syncthreads();
+    }
+    if (CSM) {
+        const int32_t n_cells = ix.grid.gx * ix.grid.gy;
+        for (int32_t c = threadIdx.x; c < n_cells; c += kQueryThreads) cand0[c] = __ldg(&ix.cand01[c].x);
         __syncthreads();
     }
     const GridParams &g = ix.grid;
@@ -1551,8 +1578,13 @@ __global__ void __launch_bounds__(kQueryThreads, MINB) k_pip_stream(const IndexV
             code[k] = (word[k] >> ((fx[k] & 15) * 2)) & 3u;
             id[k] = -1;
             if (code[k] == 1u || code[k] == 2u) {
-                const int2 cand = __ldg(ix.cand01 + (int64_t)(fy[k] >> g.rs) * g.gx + (fx[k] >> g.rs));
-                id[k] = code[k] == 1u ? cand.x : cand.y;
+                const int64_t cc = (int64_t)(fy[k] >> g.rs) * g.gx + (fx[k] >> g.rs);
+                if (CSM && code[k] == 1u) {
+                    id[k] = cand0[cc];
+                } else {
+                    const int2 cand = __ldg(ix.cand01 + cc);
+                    id[k] = code[k] == 1u ? cand.x : cand.y;
+                }
                 if (HIST && id[k] >= 0 && id[k] < n_bins) atomicAdd(&bins[id[k]], 1u);
             }
         }
@@ -1708,35 +1740,37 @@ static int query_grid(int64_t n, bool lean = false) {
 }
 // streaming kernel: exactly the resident CTAs (persistent warps, one tile of 128 points per warp and iteration)
 constexpr int32_t kHistFuseMaxBins = 12288;  // 48 KB of bins per CTA: three CTAs per SM still fit next to the queues
-template <bool LEAN, bool HIST, int MINB>
+template <bool LEAN, bool HIST, bool CSM>
 static int stream_grid(int64_t n, size_t smem_bytes) {
     static size_t attr_bytes = 0;
     if (smem_bytes > attr_bytes) {
-        cudaFuncSetAttribute(k_pip_stream<LEAN, HIST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_pip_stream<LEAN, HIST, CSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         attr_bytes = smem_bytes;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN, HIST, MINB>, kQueryThreads, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pip_stream<LEAN, HIST, CSM>, kQueryThreads, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
     (void)cudaGetLastError();
     static const int cap = env_int("GPL_PIP_STREAM_CTAS_PER_SM", 0);
     const int per_sm = cap > 0 ? std::min(cap, occ) : occ;
     const int64_t want = ceil_div(ceil_div(n, kTilePts), kStreamWarps);
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kSMs * per_sm));
 }
+constexpr int32_t kCandSmemMaxCells = 12288;  // 48 KB of candidate rows per CTA
 template <bool LEAN, bool HIST>
 static void launch_stream(const IndexView &v, const double2 *pts, const uint8_t *val, int64_t m, int32_t *first, int32_t *cnt,
                           const gpl_pip_index *idx, int vec_ok, unsigned long long *hist, int32_t n_bins, cudaStream_t stream) {
+    static const bool csm_enabled = env_int("GPL_PIP_CAND_SMEM", 1) != 0;
+    const int64_t n_cells = (int64_t)v.grid.gx * v.grid.gy;
+    if (!HIST && csm_enabled && n_cells <= kCandSmemMaxCells) {
+        const size_t smem = sizeof(StreamSmem) + sizeof(int32_t) * (size_t)n_cells;
+        k_pip_stream<LEAN, false, true><<<stream_grid<LEAN, false, true>(m, smem), kQueryThreads, smem, stream>>>(
+            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, nullptr, 0);
+        return;
+    }
     const size_t smem = sizeof(StreamSmem) + (HIST ? sizeof(unsigned int) * (size_t)n_bins : 0);
-    // resident CTAs per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers)
-    static const int minb = env_int("GPL_PIP_STREAM_MINB", GPL_PIP_STREAM_MINB);
-    if (minb >= 4)
-        k_pip_stream<LEAN, HIST, 4><<<stream_grid<LEAN, HIST, 4>(m, smem), kQueryThreads, smem, stream>>>(
-            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
-    else
-        k_pip_stream<LEAN, HIST, 3><<<stream_grid<LEAN, HIST, 3>(m, smem), kQueryThreads, smem, stream>>>(
-            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
+    k_pip_stream<LEAN, HIST, false><<<stream_grid<LEAN, HIST, false>(m, smem), kQueryThreads, smem, stream>>>(
+        v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
 }
-
 // hist (optional, device, n_geoms u64): += number of points whose first containing row is that polygon
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
               int32_t *first_dev, int32_t *count_dev, cudaStream_t stream, unsigned long long *hist = nullptr) {
@@ -1985,7 +2019,8 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     Scratch<PartHeader> hdr;
     Scratch<GridParams> gp;
     Scratch<int32_t> nb, cell_count, cell_cursor, bcount, bcursor, fast_c, fast_slots;
-    Scratch<int2> side_count;
+    Scratch<int2> side_count, ovf_off;
+    Scratch<int32_t> bucket_part;
     Scratch<int64_t> partial;
     Scratch<unsigned long long> acc;
     TRYF(hdr.get(ctx, (size_t)Pa));
@@ -1995,11 +2030,14 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(cell_count.get(ctx, (size_t)n_cells + 1));
     TRYF(bcount.get(ctx, (size_t)a.NB_cap + 1));
     TRYF(side_count.get(ctx, (size_t)a.NB_cap + 1));
+    TRYF(ovf_off.get(ctx, (size_t)a.NB_cap + 1));
+    TRYF(bucket_part.get(ctx, (size_t)a.NB_cap + 1));
     TRYF(fast_c.get(ctx, (size_t)Pa + 1));
     TRYF(fast_slots.get(ctx, (size_t)Pa + 1));
     TRYF(acc.get(ctx, ACC_COUNT));
     a.hdr = hdr.p, a.gp = gp.p, a.nb = nb.p, a.partial = partial.p, a.cell_count = cell_count.p, a.bcount = bcount.p;
     a.side_count = side_count.p, a.fast_c = fast_c.p, a.fast_slots = fast_slots.p, a.acc = acc.p;
+    a.ovf_off = ovf_off.p, a.bucket_part = bucket_part.p;
     CUDAF(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * ACC_COUNT, st));
     {
         void *args[] = {&a};
@@ -2204,6 +2242,46 @@ extern "C" int gpl_contains_join_pairs(gpl_ctx *ctx, const gpl_pip_index *idx, c
         GPL_CUDA(cudaMemcpyAsync(lhs, pl, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
         GPL_CUDA(cudaMemcpyAsync(rhs, pr, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPL_OK;
+}
+
+// result of a join: defined in k_pairs.cu (gpl_spatial_join); the points-in-polygons join can return the same object
+struct gpl_pairs {
+    gpl_ctx *ctx = nullptr;
+    uint64_t *lhs = nullptr, *rhs = nullptr;  // device
+    int64_t n = 0;
+};
+extern "C" int gpl_contains_join_pairs_array(gpl_ctx *ctx, const gpl_pip_index *idx, const gpl_array *points, gpl_pairs **out) {
+    GPL_REQUIRE(ctx && idx && points && out, GPL_ERR_INVALID_ARG, "gpl_contains_join_pairs_array: NULL argument");
+    GPL_REQUIRE(points->type == GPL_POINT, GPL_ERR_INVALID_TYPE, "Expected Point (found geometry type %d)", points->type);
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    gpl_pairs *res = new gpl_pairs();
+    res->ctx = ctx;
+    *out = res;
+    const int64_t n = points->n_geoms;
+    if (n == 0) return GPL_OK;
+    Scratch<int32_t> ids, cnt;
+    Scratch<int64_t> off;
+    GPL_TRY(ids.get(ctx, (size_t)n));
+    GPL_TRY(cnt.get(ctx, (size_t)n));
+    GPL_TRY(off.get(ctx, (size_t)n + 2));
+    GPL_TRY(pip_query(ctx, idx, points->xy, points->validity, n, ids.p, cnt.p, ctx->stream));
+    GPL_TRY((exclusive_scan<int32_t, int64_t>(ctx, cnt.p, n, off.p, off.p + n + 1)));
+    int64_t total = 0;
+    GPL_CUDA(cudaMemcpyAsync(&total, off.p + n + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (total == 0) return GPL_OK;
+    void *pl = nullptr, *pr = nullptr;
+    GPL_TRY(ctx->alloc(sizeof(uint64_t) * (size_t)total, &pl));
+    res->lhs = (uint64_t *)pl;
+    GPL_TRY(ctx->alloc(sizeof(uint64_t) * (size_t)total, &pr));
+    res->rhs = (uint64_t *)pr;
+    res->n = total;
+    k_pip_query<1><<<query_grid(n), kQueryThreads, 0, ctx->stream>>>(view_of(idx), reinterpret_cast<const double2 *>(points->xy), points->validity, n,
+                                                                nullptr, nullptr, off.p, res->lhs, res->rhs, 0, nullptr, nullptr, 0);
+    ctx->launches++;
+    GPL_CUDA(cudaGetLastError());
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
 }

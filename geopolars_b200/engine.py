@@ -408,11 +408,41 @@ def intersects(a: DeviceArray, b: DeviceArray) -> np.ndarray:
     return _bits(bm, n)
 
 
-def contains(polygons: DeviceArray, points: DeviceArray) -> np.ndarray:
-    n = len(polygons)
+def contains(a: DeviceArray, b: DeviceArray) -> np.ndarray:
+    """row-wise a[i].contains(b[i]): (Multi)Polygon / (Multi)LineString x Point, or (Multi)Polygon x Polygon (the pairs the
+    reference's join dispatches, spatial_index.rs:89-135)"""
+    n = len(a)
     bm = np.zeros((n + 7) // 8, dtype=np.uint8)
-    check(polygons.ctx.lib.gpl_contains(polygons.ctx._h, polygons._h, points._h, _np_ptr(bm), GPL_HOST))
+    fn = a.ctx.lib.gpl_contains_polygon if b.type == GeometryType.POLYGON else a.ctx.lib.gpl_contains
+    check(fn(a.ctx._h, a._h, b._h, _np_ptr(bm), GPL_HOST))
     return _bits(bm, n)
+
+
+PREDICATES = {"intersects": 0, "contains": 1}
+
+
+def _pairs_to_host(ctx: Context, h) -> Tuple[np.ndarray, np.ndarray]:
+    try:
+        n = int(ctx.lib.gpl_pairs_count(h))
+        lhs = np.empty(n, dtype=np.uint64)
+        rhs = np.empty(n, dtype=np.uint64)
+        if n:
+            check(ctx.lib.gpl_pairs_copy(ctx._h, h, _np_ptr(lhs), _np_ptr(rhs), GPL_HOST))
+    finally:
+        ctx.lib.gpl_pairs_free(h)
+    order = np.lexsort((rhs, lhs))  # the reference's order is unspecified (tree traversal): sorted by (lhs, rhs) here
+    return lhs[order], rhs[order]
+
+
+def spatial_join(lhs: DeviceArray, rhs: DeviceArray, predicate: str = "intersects") -> Tuple[np.ndarray, np.ndarray]:
+    """(lhs_index, rhs_index) pairs of spatial_join(lhs, rhs, SpatialJoinArgs{predicate, ..}) for any two geometry columns
+    (spatial_index.rs:37-157): envelope candidates + the reference's type-pair dispatch."""
+    p = PREDICATES.get(str(predicate).lower())
+    if p is None:
+        raise ValueError("predicate must be 'intersects' or 'contains'")
+    h = C.c_void_p()
+    check(lhs.ctx.lib.gpl_spatial_join(lhs.ctx._h, lhs._h, rhs._h, p, C.byref(h)))
+    return _pairs_to_host(lhs.ctx, h)
 
 
 def geom_type(a: DeviceArray) -> np.ndarray:
@@ -523,6 +553,12 @@ class PipIndex:
             check(self.ctx.lib.gpl_contains_join_pairs(self.ctx._h, self._h, _np_ptr(pts), n, _np_ptr(lhs), _np_ptr(rhs),
                                                        C.byref(total), GPL_HOST))
         return lhs, rhs
+
+    def pairs_array(self, points: DeviceArray) -> Tuple[np.ndarray, np.ndarray]:
+        """the same pair list for a Point column that already lives in HBM (no host round trip of the points)"""
+        h = C.c_void_p()
+        check(self.ctx.lib.gpl_contains_join_pairs_array(self.ctx._h, self._h, points._h, C.byref(h)))
+        return _pairs_to_host(self.ctx, h)
 
     def free(self) -> None:
         if getattr(self, "_h", None) and self.ctx._h:

@@ -227,7 +227,7 @@ class GeoRustSeries:
 
     # -- additions: binary predicates (planned-only in the reference docs, geoseries.rst:47-64) ----------
     def contains(self, other: GeoSeries):
-        """row-wise: self[i] ((Multi)Polygon or (Multi)LineString) contains other[i] (Point)"""
+        """row-wise: self[i] ((Multi)Polygon or (Multi)LineString) contains other[i] (Point), or (Multi)Polygon contains Polygon"""
         return _pa().array(E.contains(self._d(), other.device))
 
     def intersects(self, other: GeoSeries):
@@ -235,25 +235,30 @@ class GeoRustSeries:
         return _pa().array(E.intersects(self._d(), other.device))
 
 
-def spatial_join(points: GeoSeries, polygons: GeoSeries, how: str = "inner"):
-    """Points x polygons contains-join: the (lhs_index, rhs_index) pairs the reference builds before its
-    polars joins (geopolars/src/spatial_index.rs:74-157).  how='inner' -> pairs of matching rows;
-    how='left' -> every point once per match, or once with rhs = -1 (null) when it has none, which is the
-    row set of the reference's Left join (9 rows for the 9-point test, spatial_index.rs:483-484)."""
+def spatial_join(lhs: GeoSeries, rhs: GeoSeries, how: str = "inner", predicate: str = "intersects"):
+    """spatial_join(lhs, rhs, SpatialJoinArgs{join_type, predicate}) (geopolars/src/spatial_index.rs:37-204): the
+    (lhs_index, rhs_index) pairs the reference builds before its polars joins (:139-157), for any two geometry
+    columns.  Candidates are the pairs whose envelopes intersect, the exact test is the reference's type-pair dispatch
+    (:89-137; Point x (Multi)Polygon uses contains(point) whatever the predicate).  how='inner' -> matching pairs;
+    how='left' -> every lhs row once per match, or once with rhs = -1 (null) when it has none — the row set of the
+    reference's Left join (9 rows for the 9-point test, :483-484).  Points x (Multi)Polygons run on the points-in-polygons
+    index (the north-star path) without moving the device-resident point column; everything else on gpl_spatial_join."""
     if how not in ("inner", "left"):
         raise ValueError("how must be 'inner' or 'left'")
-    idx = E.PipIndex(polygons.device)
-    pts = points.device.to_host()
-    lhs, rhs = idx.pairs(pts.xy)
-    lhs = lhs.astype(np.int64)
-    rhs = rhs.astype(np.int64)
+    lt, rt = lhs.device.type, rhs.device.type
+    if lt == E.GeometryType.POINT and rt in (E.GeometryType.POLYGON, E.GeometryType.MULTIPOLYGON):
+        a, b = E.PipIndex(rhs.device).pairs_array(lhs.device)
+    else:
+        a, b = E.spatial_join(lhs.device, rhs.device, predicate)
+    a = a.astype(np.int64)
+    b = b.astype(np.int64)
     if how == "left":
-        n = len(points)
+        n = len(lhs)
         matched = np.zeros(n, dtype=bool)
-        matched[lhs] = True
+        matched[a] = True
         miss = np.nonzero(~matched)[0]
-        lhs = np.concatenate([lhs, miss])
-        rhs = np.concatenate([rhs, np.full(len(miss), -1, dtype=np.int64)])
-        order = np.lexsort((rhs, lhs))
-        lhs, rhs = lhs[order], rhs[order]
-    return lhs, rhs
+        a = np.concatenate([a, miss])
+        b = np.concatenate([b, np.full(len(miss), -1, dtype=np.int64)])
+        order = np.lexsort((b, a))
+        a, b = a[order], b[order]
+    return a, b

@@ -69,7 +69,8 @@ typedef enum gpl_origin { GPL_ORIGIN_CENTROID = 0, GPL_ORIGIN_CENTER = 1, GPL_OR
 
 typedef struct gpl_ctx gpl_ctx;             /* one per (host thread, device) */
 typedef struct gpl_array gpl_array;         /* GeoArrow geometry array resident in HBM */
-typedef struct gpl_pip_index gpl_pip_index; /* polygon-side index of a contains join */
+typedef struct gpl_pip_index gpl_pip_index;
+typedef struct gpl_pairs gpl_pairs;         /* (lhs_index, rhs_index) pair list of a join, resident on the device */ /* polygon-side index of a contains join */
 
 /* Raw GeoArrow buffers (the zero-dependency form of an Arrow array; replaces the WKB BinaryArray the
  * reference re-parses on every op, util.rs:27-37).
@@ -261,6 +262,9 @@ int gpl_contains_join_array(gpl_ctx *ctx, const gpl_pip_index *idx, const gpl_ar
  * (point, polygon).  Call with lhs == NULL to get *n_pairs, then with buffers of that size. */
 int gpl_contains_join_pairs(gpl_ctx *ctx, const gpl_pip_index *idx, const double *points_xy, int64_t n_points,
                             uint64_t *lhs, uint64_t *rhs, int64_t *n_pairs, int mem);
+/* the same pair list for a POINT gpl_array already in HBM (null points match nothing), as a device-resident gpl_pairs
+ * (gpl_pairs_count / gpl_pairs_copy / gpl_pairs_free): no host round trip of the point column */
+int gpl_contains_join_pairs_array(gpl_ctx *ctx, const gpl_pip_index *idx, const gpl_array *points, gpl_pairs **out);
 /* host-resident points streamed through HBM in chunks with H2D / kernel / D2H overlapped on three
  * streams (the end-to-end path: PCIe-bound).  chunk_points = 0 picks a default. */
 int gpl_contains_join_host(gpl_ctx *ctx, const gpl_pip_index *idx, const double *points_xy_host, int64_t n_points,
@@ -268,6 +272,21 @@ int gpl_contains_join_host(gpl_ctx *ctx, const gpl_pip_index *idx, const double 
 /* per-polygon hit counts: counts[n_polygons] u64 += hits (config 4's all-reduce input) */
 int gpl_join_histogram(gpl_ctx *ctx, const int32_t *first_id, int64_t n_points, uint64_t *counts, int64_t n_polygons,
                        int mem);
+
+/* row-wise (Multi)Polygon.contains(Polygon) (the Predicate::Contains arms of spatial_index.rs:99-110; geo's
+ * relate(..).is_contains(), DE-9IM [T*****FF*], for valid operands): Arrow bitmap, null rows -> false. */
+int gpl_contains_polygon(gpl_ctx *ctx, const gpl_array *a, const gpl_array *b, uint8_t *out_bitmap, int mem);
+/* spatial_join(lhs, rhs, predicate) for ANY two geometry columns (spatial_index.rs:37-157): candidates = pairs whose
+ * envelopes intersect (closed intervals, :74-76), exact test by the reference's type-pair dispatch (:89-137: Point x
+ * (Multi)Polygon / (Multi)LineString in either order -> contains(point) whatever the predicate; (Multi)Polygon x Polygon ->
+ * contains or intersects; Polygon x MultiPolygon -> intersects only; every other pair of types -> no match).  The
+ * result is the pair list the reference builds at :139-157; its order is unspecified there (tree traversal) and here. */
+#define GPL_PREDICATE_INTERSECTS 0
+#define GPL_PREDICATE_CONTAINS 1
+int gpl_spatial_join(gpl_ctx *ctx, const gpl_array *lhs, const gpl_array *rhs, int predicate, gpl_pairs **out);
+int64_t gpl_pairs_count(const gpl_pairs *pairs);
+int gpl_pairs_copy(gpl_ctx *ctx, const gpl_pairs *pairs, uint64_t *lhs, uint64_t *rhs, int mem);
+void gpl_pairs_free(gpl_pairs *pairs);
 
 /* ---------------------------------------------------------------- synthetic data --------- */
 /* device-side generators, bit-identical to geopolars_b200/synth.py (SURVEY.md §8d RNG) */

@@ -155,3 +155,102 @@ def linestring_intersects_polygon(ls: Sequence[Coord], rings: Sequence[Sequence[
     if len(ls) < 2 or not rr:
         return False
     return any(linestrings_intersect(ls, r) for r in rr) or closed_polygon_has(ls[0], rr)
+
+
+# ---- (Multi)Polygon contains Polygon: the closed-region definition on the exact arrangement -------------------
+def _region_pos(p, members) -> int:
+    """0 exterior / 1 boundary / 2 interior of the union of polygons `members` (each a list of rings); p may be rational"""
+    boundary = False
+    for rings in members:
+        rings = [_closed(r) for r in rings if len(r) > 0]
+        if not rings:
+            continue
+        pe = ring_position(p, rings[0])
+        if pe == 0:
+            continue
+        if pe == 1:
+            boundary = True
+            continue
+        in_hole = False
+        for h in rings[1:]:
+            ph = ring_position(p, h)
+            if ph == 2:
+                in_hole = True
+                break
+            if ph == 1:
+                in_hole = boundary = True
+                break
+        if not in_hole:
+            return 2
+    return 1 if boundary else 0
+
+
+def _edges(members):
+    for rings in members:
+        for r in rings:
+            c = _closed(r)
+            for s, e in zip(c[:-1], c[1:]):
+                if tuple(s) != tuple(e):
+                    yield s, e
+
+
+def _cut_params(u, v, others):
+    """parameters in [0,1] at which the segment u-v meets the segments `others` (crossings and overlap ends), exact"""
+    ux, uy, vx, vy = map(F, (*u, *v))
+    rx, ry = vx - ux, vy - uy
+    rr = rx * rx + ry * ry
+    ts = {F(0), F(1)}
+    for s, e in others:
+        sx, sy, ex, ey = map(F, (*s, *e))
+        qx, qy = ex - sx, ey - sy
+        den = rx * qy - ry * qx
+        wx, wy = sx - ux, sy - uy
+        if den != 0:
+            t = (wx * qy - wy * qx) / den
+            w = (wx * ry - wy * rx) / den
+            if 0 <= t <= 1 and 0 <= w <= 1:
+                ts.add(t)
+        elif wx * ry - wy * rx == 0:  # collinear: the ends of the other segment
+            for px, py in ((sx, sy), (ex, ey)):
+                t = ((px - ux) * rx + (py - uy) * ry) / rr
+                if 0 <= t <= 1:
+                    ts.add(t)
+    return sorted(ts)
+
+
+def _pieces_midpoints(u, v, others):
+    ts = _cut_params(u, v, others)
+    ux, uy, vx, vy = map(F, (*u, *v))
+    for a, b in zip(ts[:-1], ts[1:]):
+        m = (a + b) / 2
+        yield (ux + m * (vx - ux), uy + m * (vy - uy))
+
+
+def region_contains_polygon(a_members, b_rings) -> bool:
+    """closure(A) contains B and the interiors meet (DE-9IM T*****FF*) for VALID operands, on the exact arrangement:
+    every piece of boundary(B) between consecutive meetings with boundary(A) has its midpoint in closure(A); no piece of
+    boundary(A) has its midpoint strictly inside B; and a point just beside boundary(B), on B's interior side, is
+    strictly inside A."""
+    b_members = [b_rings]
+    if not a_members or not b_rings or len(_closed(b_rings[0])) < 4:
+        return False
+    a_edges, b_edges = list(_edges(a_members)), list(_edges(b_members))
+    if not a_edges or not b_edges:
+        return False
+    for u, v in b_edges:
+        for m in _pieces_midpoints(u, v, a_edges):
+            if _region_pos(m, a_members) == 0:
+                return False
+    for s, e in a_edges:
+        for m in _pieces_midpoints(s, e, b_edges):
+            if _region_pos(m, b_members) == 2:
+                return False
+    u, v = b_edges[0]
+    (mx, my), = list(_pieces_midpoints(u, v, []))
+    dx, dy = F(v[0]) - F(u[0]), F(v[1]) - F(u[1])
+    tiny = F(1, 2 ** 400)
+    for side in (1, -1):
+        q = (mx - side * tiny * dy, my + side * tiny * dx)
+        if _region_pos(q, b_members) == 2:
+            return _region_pos(q, a_members) == 2
+    return False

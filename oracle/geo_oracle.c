@@ -953,6 +953,196 @@ void og_contains_rowwise(const og_array *a, const double *pts_xy, const uint8_t 
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Polygon / MultiPolygon contains Polygon — spatial_index.rs:99-110 (`poly_lhs.contains(poly_rhs)`)        */
+/* ------------------------------------------------------------------------------------------- */
+/* geo 0.27 contains/polygon.rs (recalled): `impl_contains_from_relate!(Polygon<T>, [.. Polygon ..])`, i.e.
+ * self.relate(rhs).is_contains() = DE-9IM [T*****FF*]: the interiors meet and no point of rhs (interior or boundary)
+ * lies in the exterior of self.  For VALID operands (rings simple, holes inside, members of a MultiPolygon touching in
+ * points only) that is:   B subset of closure(A)   and   interior(A) meets interior(B).   geo evaluates it on its
+ * topology graph; this restatement decides the same three conditions with exact orientation signs only:
+ *   C1  boundary(B) inside closure(A):  no B edge leaves A.  A straight B edge can only leave closure(A) (i) at its start,
+ *       (ii) by crossing an A edge properly (both interiors) or (iii) at an A vertex lying inside it; so it suffices that
+ *       the edge, just after its start and just after every A vertex on it, is not in the exterior, and that no proper
+ *       crossing exists (unless an A vertex sits exactly on the crossing — members touching there — which (iii) judges).
+ *   C2  no point of boundary(A) is strictly inside B (otherwise a hole of A, or a gap between touching members, lies in B):
+ *       the same three events with the roles swapped.
+ *   C3  anchor: with C1 and C2 the connected interior of B is entirely inside or entirely outside A; one point just
+ *       beside the first edge of B, on B's own interior side, decides.
+ * "Just after / just beside" are SYMBOLIC points q = x + eps (v - x) + eps^2 side L(v - x), L = left normal, eps an
+ * infinitesimal: every comparison geo's coord_pos_relative_to_ring makes is evaluated on x first and, on a tie, on the
+ * eps and eps^2 terms, whose signs are exact (coordinate comparisons and orient2d of input vertices).
+ * Parity unpinned (the reference holds no vector for it); refereed by oracle/exact.py's rational arrangement form. */
+typedef struct {
+    double xx, xy, vx, vy;
+    int side; /* 0: on the open segment x->v just after x; +1 / -1: just left / right of it */
+} symq_t;
+static inline int cmpd(double a, double b) { return (a > b) - (a < b); }
+static inline int sgnd(double a) { return (a > 0.0) - (a < 0.0); }
+/* sign of (cy - q.y),  q.y = x.y + eps (v.y - x.y) + eps^2 side (v.x - x.x) */
+static int sym_cmp_y(const symq_t *q, double cy) {
+    int c = cmpd(cy, q->xy);
+    if (c) return c;
+    c = -cmpd(q->vy, q->xy);
+    if (c) return c;
+    return -q->side * cmpd(q->vx, q->xx);
+}
+/* sign of (cx - q.x),  q.x = x.x + eps (v.x - x.x) - eps^2 side (v.y - x.y) */
+static int sym_cmp_x(const symq_t *q, double cx) {
+    int c = cmpd(cx, q->xx);
+    if (c) return c;
+    c = -cmpd(q->vx, q->xx);
+    if (c) return c;
+    return q->side * cmpd(q->vy, q->xy);
+}
+/* sign of orient2d(s, e, q): affine in q; the eps term is orient2d(s,e,v) once orient2d(s,e,x) = 0, the eps^2 term is
+ * side * dot(e - s, v - x), and with s, e, x, v collinear the dot product's sign is a product of coordinate orders */
+static int sym_orient(const double *s, const double *e, const symq_t *q) {
+    int o = sgnd(og_orient2d(s[0], s[1], e[0], e[1], q->xx, q->xy));
+    if (o) return o;
+    o = sgnd(og_orient2d(s[0], s[1], e[0], e[1], q->vx, q->vy));
+    if (o || !q->side) return o;
+    int d1, d2;
+    if (e[0] != s[0]) d1 = cmpd(e[0], s[0]), d2 = cmpd(q->vx, q->xx);
+    else d1 = cmpd(e[1], s[1]), d2 = cmpd(q->vy, q->xy);
+    return q->side * d1 * d2;
+}
+static int sym_between_x(const symq_t *q, double b1, double b2) { /* value_in_between(q.x, b1, b2) */
+    if (b1 < b2) return sym_cmp_x(q, b1) <= 0 && sym_cmp_x(q, b2) >= 0;
+    return sym_cmp_x(q, b2) <= 0 && sym_cmp_x(q, b1) >= 0;
+}
+/* coord_pos_relative_to_ring (the loop of coord_pos_ring above) for a symbolic point */
+static int sym_ring_pos(const symq_t *q, const double *xy, int64_t n) {
+    if (n < 2) return POS_OUTSIDE; /* q never equals a vertex */
+    chain_t c = mk_ring(xy, 0, n);
+    int64_t m = chain_coords(&c);
+    int wn = 0;
+    for (int64_t i = 0; i + 1 < m; ++i) {
+        const double *s = chain_at(&c, i), *e = chain_at(&c, i + 1);
+        int cs = sym_cmp_y(q, s[1]), ce = sym_cmp_y(q, e[1]); /* signs of s.y - q.y, e.y - q.y */
+        if (cs <= 0) {
+            if (ce >= 0) {
+                int o = sym_orient(s, e, q);
+                if (o > 0 && ce != 0) wn += 1;
+                else if (o == 0 && sym_between_x(q, s[0], e[0])) return POS_BOUNDARY;
+            }
+        } else if (ce <= 0) {
+            int o = sym_orient(s, e, q);
+            if (o < 0) wn -= 1;
+            else if (o == 0 && sym_between_x(q, s[0], e[0])) return POS_BOUNDARY;
+        }
+    }
+    return wn ? POS_INSIDE : POS_OUTSIDE;
+}
+/* position of q in the union of the polygon members [m0, m1) of the POLYGON view `a` */
+static int sym_region_pos(const og_array *a, int64_t m0, int64_t m1, const symq_t *q) {
+    int boundary = 0;
+    for (int64_t m = m0; m < m1; ++m) {
+        int64_t r0 = a->geom_off[m], r1 = a->geom_off[m + 1];
+        if (r1 <= r0) continue;
+        int pe = sym_ring_pos(q, a->xy + 2 * a->ring_off[r0], a->ring_off[r0 + 1] - a->ring_off[r0]);
+        if (pe == POS_OUTSIDE) continue;
+        if (pe == POS_BOUNDARY) {
+            boundary = 1;
+            continue;
+        }
+        int in_hole = 0;
+        for (int64_t r = r0 + 1; r < r1 && !in_hole; ++r) {
+            int ph = sym_ring_pos(q, a->xy + 2 * a->ring_off[r], a->ring_off[r + 1] - a->ring_off[r]);
+            if (ph == POS_INSIDE) in_hole = 1;
+            else if (ph == POS_BOUNDARY) in_hole = 1, boundary = 1;
+        }
+        if (!in_hole) return POS_INSIDE;
+    }
+    return boundary ? POS_BOUNDARY : POS_OUTSIDE;
+}
+/* c strictly between u and v on their common line (c collinear with u, v by the caller's orient2d == 0) */
+static int strictly_between(const double *c, const double *u, const double *v) {
+    if (u[0] != v[0]) return (c[0] > fmin(u[0], v[0])) && (c[0] < fmax(u[0], v[0]));
+    return (c[1] > fmin(u[1], v[1])) && (c[1] < fmax(u[1], v[1]));
+}
+/* is some vertex of the members [m0,m1) of `a` on both lines u-v and s-e (i.e. exactly at their crossing)? */
+static int vertex_at_crossing(const og_array *a, int64_t m0, int64_t m1, const double *u, const double *v, const double *s, const double *e) {
+    for (int64_t r = a->geom_off[m0]; r < a->geom_off[m1]; ++r)
+        for (int64_t c = a->ring_off[r]; c < a->ring_off[r + 1]; ++c) {
+            const double *w = a->xy + 2 * c;
+            if (og_orient2d(u[0], u[1], v[0], v[1], w[0], w[1]) == 0.0 && og_orient2d(s[0], s[1], e[0], e[1], w[0], w[1]) == 0.0) return 1;
+        }
+    return 0;
+}
+/* the edges of region X = members [x0,x1) of view x must not reach into FORBIDDEN (POS_OUTSIDE or POS_INSIDE) of region
+ * Y = members [y0,y1) of view y; check_cross: proper crossings make it fail (C1) */
+static int edges_avoid(const og_array *x, int64_t x0, int64_t x1, const og_array *y, int64_t y0, int64_t y1, int forbidden, int check_cross) {
+    for (int64_t rx = x->geom_off[x0]; rx < x->geom_off[x1]; ++rx) {
+        chain_t cx = mk_ring(x->xy, x->ring_off[rx], x->ring_off[rx + 1]);
+        int64_t nx = chain_coords(&cx);
+        for (int64_t i = 0; i + 1 < nx; ++i) {
+            const double *u = chain_at(&cx, i), *v = chain_at(&cx, i + 1);
+            if (u[0] == v[0] && u[1] == v[1]) continue;
+            symq_t q = {u[0], u[1], v[0], v[1], 0};
+            if (sym_region_pos(y, y0, y1, &q) == forbidden) return 0;
+            for (int64_t ry = y->geom_off[y0]; ry < y->geom_off[y1]; ++ry) {
+                chain_t cy = mk_ring(y->xy, y->ring_off[ry], y->ring_off[ry + 1]);
+                int64_t ny = chain_coords(&cy);
+                for (int64_t j = 0; j + 1 < ny; ++j) {
+                    const double *s = chain_at(&cy, j), *e = chain_at(&cy, j + 1);
+                    int o1 = sgnd(og_orient2d(u[0], u[1], v[0], v[1], s[0], s[1]));
+                    if (check_cross && !(s[0] == e[0] && s[1] == e[1])) {
+                        int o2 = sgnd(og_orient2d(u[0], u[1], v[0], v[1], e[0], e[1]));
+                        if (o1 * o2 < 0) {
+                            int o3 = sgnd(og_orient2d(s[0], s[1], e[0], e[1], u[0], u[1])), o4 = sgnd(og_orient2d(s[0], s[1], e[0], e[1], v[0], v[1]));
+                            if (o3 * o4 < 0 && !vertex_at_crossing(y, y0, y1, u, v, s, e)) return 0;
+                        }
+                    }
+                    if (o1 == 0 && strictly_between(s, u, v)) { /* a vertex of Y inside this edge: the part after it */
+                        symq_t q2 = {s[0], s[1], v[0], v[1], 0};
+                        if (sym_region_pos(y, y0, y1, &q2) == forbidden) return 0;
+                    }
+                }
+            }
+        }
+    }
+    return 1;
+}
+/* A = members [a0,a1) of the POLYGON view `a` (one for Polygon, the parts of a MultiPolygon); B = polygon b of view `bv` */
+static int region_contains_polygon(const og_array *a, int64_t a0, int64_t a1, const og_array *bv, int64_t b) {
+    int64_t br0 = bv->geom_off[b], br1 = bv->geom_off[b + 1];
+    if (a1 <= a0 || br1 <= br0 || bv->ring_off[br0 + 1] - bv->ring_off[br0] < 3) return 0;
+    if (!edges_avoid(bv, b, b + 1, a, a0, a1, POS_OUTSIDE, 1)) return 0; /* C1 */
+    if (!edges_avoid(a, a0, a1, bv, b, b + 1, POS_INSIDE, 0)) return 0;  /* C2 */
+    chain_t ce = mk_ring(bv->xy, bv->ring_off[br0], bv->ring_off[br0 + 1]);
+    int64_t n = chain_coords(&ce);
+    for (int64_t i = 0; i + 1 < n; ++i) { /* C3: first non-degenerate edge of B's exterior */
+        const double *u = chain_at(&ce, i), *v = chain_at(&ce, i + 1);
+        if (u[0] == v[0] && u[1] == v[1]) continue;
+        symq_t q = {u[0], u[1], v[0], v[1], 1};
+        if (sym_region_pos(bv, b, b + 1, &q) != POS_INSIDE) {
+            q.side = -1;
+            if (sym_region_pos(bv, b, b + 1, &q) != POS_INSIDE) return 0; /* no interior beside its own boundary: degenerate */
+        }
+        return sym_region_pos(a, a0, a1, &q) == POS_INSIDE;
+    }
+    return 0;
+}
+/* row-wise: a POLYGON or MULTIPOLYGON, b POLYGON (the pairs spatial_index.rs:99-115 dispatches with Predicate::Contains) */
+int og_contains_polygon_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads) {
+    int nt = resolve_threads(threads);
+    (void)nt;
+    if (a->n != b->n || (a->type != OG_POLYGON && a->type != OG_MULTIPOLYGON) || b->type != OG_POLYGON) return -1;
+    og_array va = *a;
+    if (a->type == OG_MULTIPOLYGON) va.type = OG_POLYGON, va.geom_off = a->part_off, va.part_off = NULL;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 64)
+    for (int64_t i = 0; i < a->n; ++i) {
+        uint8_t r = 0;
+        if (is_valid(a, i) && is_valid(b, i)) {
+            int64_t m0 = a->type == OG_MULTIPOLYGON ? a->geom_off[i] : i, m1 = a->type == OG_MULTIPOLYGON ? a->geom_off[i + 1] : i + 1;
+            r = (uint8_t)region_contains_polygon(&va, m0, m1, b, i);
+        }
+        out[i] = r;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* distance — GeoSeries::distance geoseries.rs:141-146 ; geo euclidean_distance.rs +              */
 /* geo-types private_utils.rs recalled                                                          */
 /* ------------------------------------------------------------------------------------------- */

@@ -96,6 +96,8 @@ void og_contains_join(const og_array *polys, const double *pts_xy, int64_t n_pts
  * MultiPolygon arrays (geo Intersects; spatial_index.rs:102-123 call sites) -> 0/1 bytes */
 void og_intersects_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads);
 /* row-wise `a[i] contains point i` for (Multi)Polygon and (Multi)LineString rows (spatial_index.rs:91-96,125-135) */
+/* (Multi)Polygon.contains(Polygon) row-wise (spatial_index.rs:99-110; geo relate().is_contains(), recalled): 0/1 bytes */
+int og_contains_polygon_rowwise(const og_array *a, const og_array *b, uint8_t *out, int threads);
 void og_contains_rowwise(const og_array *a, const double *pts_xy, const uint8_t *pts_valid, uint8_t *out, int threads);
 /* row-wise euclidean distance (geo EuclideanDistance) for Point/LineString/Polygon pairs */
 int og_distance_rowwise(const og_array *a, const og_array *b, double *out, int threads);

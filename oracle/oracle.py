@@ -270,6 +270,17 @@ def contains_rowwise(a: OGArray, pts_xy: np.ndarray, threads: int = 1) -> np.nda
     return out.astype(bool)
 
 
+def contains_polygon_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
+    """(Multi)Polygon.contains(Polygon), row-wise (spatial_index.rs:99-110)"""
+    sa, ka = a._c()
+    sb, kb = b._c()
+    out = np.zeros(len(a), dtype=np.uint8)
+    rc = lib().og_contains_polygon_rowwise(C.byref(sa), C.byref(sb), _p(out), C.c_int(threads))
+    if rc != 0:
+        raise ValueError("contains: expected (Multi)Polygon x Polygon columns of equal length")
+    return out.astype(bool)
+
+
 def distance_rowwise(a: OGArray, b: OGArray, threads: int = 1) -> np.ndarray:
     sa, ka = a._c()
     sb, kb = b._c()

@@ -61,34 +61,25 @@ def test_distance_every_type_pair(ctx, og, conv, ka, kb):
 
 
 def test_distance_multipolygon_datasets(ctx, og, conv):
-    """the reference's bundled MultiPolygon columns against themselves shifted by one row, and against their centroids"""
-    import os
-
+    """the reference's bundled (Multi)Polygon columns: every row against the centroid of the NEXT row (MultiPolygon x Point)
+    and against itself (MultiPolygon x MultiPolygon -> 0: a geometry intersects itself)"""
     from geopolars_b200 import engine as E
-
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "nybb.npz"), allow_pickle=True)
     from test_oracle_cpu import load
 
     for name in ("nybb", "naturalearth_lowres"):
         arr, _ = load(name)
         d = ctx.upload(arr)
-        n = len(arr)
-        perm = np.roll(np.arange(n), 1)
-        shifted = GeoArrowArray.from_shapes(arr.type, [None] * 0) if n == 0 else None
-        # row-rolled copy built on the host from the nested lists
-        rows = arr.to_shapes() if hasattr(arr, "to_shapes") else None
-        if rows is None:
-            pytest.skip("GeoArrowArray.to_shapes unavailable")
-        rolled = GeoArrowArray.from_shapes(arr.type, [rows[i] for i in perm])
-        want = og.distance_rowwise(conv(arr), conv(rolled), threads=0)
-        got, valid = E.distance(d, ctx.upload(rolled))
-        ok = ~np.isnan(want)
-        assert np.array_equal(valid, ok) and rel_close(got[ok], want[ok], 1e-9)
-        cen = E.centroid(d)
         cw, cv = og.centroid(conv(arr))
-        want_c = og.distance_rowwise(conv(arr), conv(GeoArrowArray.points(cw)), threads=0)
-        got_c, _ = E.distance(d, cen)
-        assert rel_close(got_c, want_c, 1e-9)
+        assert cv.all()
+        pts = GeoArrowArray.points(np.roll(cw, 1, axis=0))
+        want = og.distance_rowwise(conv(arr), conv(pts), threads=0)
+        got, valid = E.distance(d, ctx.upload(pts))
+        assert valid.all() and rel_close(got, want, 1e-9) and (want > 0).sum() > len(arr) // 2
+        got2, valid2 = E.distance(ctx.upload(pts), d)  # symmetric impl
+        assert valid2.all() and rel_close(got2, want, 1e-9)
+        self_d, self_ok = E.distance(d, d)
+        want_self = og.distance_rowwise(conv(arr), conv(arr), threads=0)
+        assert np.array_equal(self_ok, ~np.isnan(want_self)) and (self_d[self_ok] == 0.0).all()
 
 
 def test_polygon_pairs_against_exact_rational_referee(ctx):

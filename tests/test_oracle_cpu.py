@@ -328,3 +328,47 @@ def test_oracle_properties_distance_hull_simplify(og, conv):
         assert keep[off[:-1]].all() and keep[off[1:] - 1].all()  # end points always survive
         assert keep.sum() <= prev.sum()
         prev = keep
+
+
+def test_polygon_contains_polygon_oracle_vs_exact_referee(og, conv):
+    """(Multi)Polygon.contains(Polygon) (spatial_index.rs:99-110; geo relate().is_contains(), recalled — parity unpinned by
+    the reference): the oracle's orientation-sign procedure against the exact-rational arrangement form of the same
+    definition (closure(A) contains B, interiors meet), on crafted touching / equal / hole / notch cases and random valid
+    lattice polygons"""
+    import shapes
+    from oracle import exact
+
+    rng = np.random.default_rng(5)
+    A, B = shapes.contains_cases(rng, 250)
+    ga, gb = GeoArrowArray.from_shapes(GeometryType.POLYGON, A), GeoArrowArray.from_shapes(GeometryType.POLYGON, B)
+    got = og.contains_polygon_rowwise(conv(ga), conv(gb), threads=0)
+    ref = np.array([exact.region_contains_polygon([a], b) for a, b in zip(A, B)])
+    assert np.array_equal(got, ref)
+    assert got[:18].tolist() == [True, True, True, False, False, False, True, True, True, True, True, True, False, False, False, True, True, True]
+    assert 40 < got.sum() < len(got) - 40
+    MA, MB = shapes.multi_contains_cases()
+    ma, mb = GeoArrowArray.from_shapes(GeometryType.MULTIPOLYGON, MA), GeoArrowArray.from_shapes(GeometryType.POLYGON, MB)
+    gm = og.contains_polygon_rowwise(conv(ma), conv(mb))
+    assert gm.tolist() == [exact.region_contains_polygon(a, b) for a, b in zip(MA, MB)] == [True, True, False, True, True, False, False]
+
+
+def test_multi_distance_is_the_minimum_over_members(og, conv):
+    """GeoSeries::distance with Multi* operands (geo's impl for iterable geometries, recalled): the minimum over the
+    members, f64::MAX for an empty collection; checked against a brute-force segment scan on the reference's nybb rows"""
+    arr, _ = load("nybb")
+    cw, cv = og.centroid(conv(arr))
+    pts = GeoArrowArray.points(np.roll(cw, 1, axis=0))
+    d = og.distance_rowwise(conv(arr), conv(pts), threads=0)
+    for i in range(len(arr)):
+        p, best = pts.xy[i], np.inf
+        for part in range(arr.geom_off[i], arr.geom_off[i + 1]):
+            for r in range(arr.part_off[part], arr.part_off[part + 1]):
+                c = arr.xy[arr.ring_off[r] : arr.ring_off[r + 1]]
+                a, ab = c[:-1], c[1:] - c[:-1]
+                L = (ab * ab).sum(1)
+                t = np.clip(((p - a) * ab).sum(1) / np.where(L > 0, L, 1), 0, 1)
+                best = min(best, np.hypot(*(p - (a + t[:, None] * ab)).T).min())
+        assert abs(best - d[i]) <= 1e-9 * best
+    empty = GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, [[], [(1.0, 1.0), (4.0, 5.0)]])
+    q = GeoArrowArray.points(np.array([[0.0, 0.0], [1.0, 1.0]]))
+    assert og.distance_rowwise(conv(empty), conv(q)).tolist() == [1.7976931348623157e308, 0.0]
