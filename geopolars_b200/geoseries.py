@@ -105,8 +105,56 @@ class GeoSeries:
         raise NotImplementedError("the GEOS backend has no operations in the reference either")
 
 
-def from_arrow(data) -> GeoSeries:
-    """geopolars.from_arrow (py-geopolars/python/geopolars/convert.py:33-56)"""
+class GeoDataFrame:
+    """The reference's GeoDataFrame (py-geopolars/python/geopolars/internals/geodataframe.py) is a polars DataFrame
+    whose `geometry` column is a GeoSeries; polars is not installed here, so this one wraps a pyarrow Table: `geometry`
+    (a GeoSeries whose buffers move to HBM on first use), `columns`, `shape`, `__getitem__`, `to_arrow`."""
+
+    def __init__(self, table, geometry: str = "geometry"):
+        pa = _pa()
+        if isinstance(table, GeoDataFrame):
+            table = table._table
+        if not isinstance(table, pa.Table):
+            raise TypeError("GeoDataFrame expects a pyarrow.Table")
+        if geometry not in table.column_names:
+            raise ValueError(f"no '{geometry}' column (columns: {', '.join(table.column_names)})")
+        self._table = table
+        self._geometry_name = geometry
+        self._geometry: Optional[GeoSeries] = None
+
+    @property
+    def geometry(self) -> GeoSeries:
+        if self._geometry is None:
+            self._geometry = GeoSeries(self._table.column(self._geometry_name), name=self._geometry_name)
+        return self._geometry
+
+    @property
+    def columns(self):
+        return list(self._table.column_names)
+
+    @property
+    def shape(self):
+        return (self._table.num_rows, self._table.num_columns)
+
+    def __len__(self) -> int:
+        return self._table.num_rows
+
+    def __getitem__(self, name: str):
+        return self.geometry if name == self._geometry_name else self._table.column(name)
+
+    def to_arrow(self):
+        return self._table
+
+    def __repr__(self) -> str:
+        return f"GeoDataFrame(shape={self.shape}, columns={self.columns})"
+
+
+def from_arrow(data):
+    """geopolars.from_arrow (py-geopolars/python/geopolars/convert.py:33-56): a Table becomes a GeoDataFrame, an Array or
+    ChunkedArray a GeoSeries"""
+    pa = _pa()
+    if isinstance(data, pa.Table):
+        return GeoDataFrame(data)
     return GeoSeries(data)
 
 

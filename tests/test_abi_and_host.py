@@ -68,3 +68,42 @@ def test_geoarrow_container_and_row_sharding():
     assert engine._origin("Centroid")[0] == 0 and engine._origin((1, 2)) == (2, 1.0, 2.0) and engine._origin({"x": 3, "y": 4})[1:] == (3.0, 4.0)
     with pytest.raises(ValueError):
         engine._origin("middle")
+
+
+def test_rust_shim_is_complete_and_binds_declared_symbols():
+    """bindings/geoseries_b200.rs (the source a maintainer drops next to geoseries.rs): every method of the reference trait
+    (geopolars/geopolars-geo/src/geoseries.rs:10-181) is implemented, and every extern "C" fn it declares is declared by
+    include/geopolars_b200.h with the same number of parameters."""
+    rs = open(os.path.join(ROOT, "bindings", "geoseries_b200.rs")).read()
+    trait_methods = ["affine_transform", "area", "centroid", "convex_hull", "envelope", "euclidean_length", "exterior", "explode",
+                     "geodesic_length", "geom_type", "is_empty", "is_ring", "rotate", "scale", "simplify", "skew", "distance",
+                     "to_crs", "to_crs_with_options", "translate", "x", "y"]
+    impl = rs[rs.index("impl GeoSeries for Series"):rs.index("pub trait GeoSeriesB200Ext")]
+    for m in trait_methods:
+        assert re.search(r"\bfn %s\(" % m, impl), f"trait method {m} missing from the Rust shim"
+    assert "todo!" not in rs and "unimplemented!" not in rs
+    hdr = open(os.path.join(ROOT, "include", "geopolars_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    block = rs[rs.index('extern "C" {'):]
+    block = block[:block.index("\n}")]
+    for name, params in re.findall(r"fn (gpl_[a-z0-9_]+)\((.*?)\)", block, flags=re.S):
+        m = re.search(r"\b%s\s*\((.*?)\)" % name, hdr, flags=re.S)
+        assert m, f"{name} is bound by the Rust shim but not declared in the header"
+        n_rs = 0 if not params.strip() else params.count(",") + 1
+        c_params = m.group(1).strip()
+        n_c = 0 if c_params in ("", "void") else c_params.count(",") + 1
+        assert n_rs == n_c, f"{name}: {n_rs} parameters in the Rust shim, {n_c} in the header"
+
+
+def test_bundled_datasets_are_arrow_ipc_files():
+    import pyarrow.ipc as ipc
+
+    from geopolars_b200 import datasets
+
+    rows = {"naturalearth_cities": 243, "nybb": 5, "naturalearth_lowres": 177, "cities": 202}
+    for name in datasets.available:
+        with open(datasets.get_path(name), "rb") as f:
+            t = ipc.open_file(f).read_all()
+        assert t.num_rows == rows[name] and t.schema.field("geometry").type == "binary"
+    with pytest.raises(ValueError):
+        datasets.get_path("nope")

@@ -158,6 +158,30 @@ def test_geoseries_accessor_surface(ctx):
         geo.geodesic_length("nope")
 
 
+def test_config1_through_read_dataset(ctx):
+    """BASELINE configs[0], literally: `read_dataset("cities").geometry.geo.centroid / .area` (datasets/__init__.py:39-42):
+    centroid(points) == points bit for bit, area == 0, 202 rows; and the Shape_Area attribute of nybb against area()"""
+    from geopolars_b200 import datasets
+    from geopolars_b200 import geoseries as G
+
+    G.set_context(ctx)
+    gdf = datasets.read_dataset("cities")
+    assert gdf.shape[0] == 202 and "geometry" in gdf.columns
+    geo = gdf.geometry.geo
+    assert np.asarray(geo.area).tolist() == [0.0] * 202
+    cen = geo.centroid.device.to_host()
+    src = gdf.geometry.device.to_host()
+    assert np.array_equal(cen.xy, src.xy)
+    assert len(datasets.read_dataset("naturalearth_cities")) == 243  # py-geopolars/tests/unit/internals/test_geoseries.py:4-5
+    nybb = datasets.read_dataset("nybb")
+    a = np.asarray(nybb.geometry.geo.area)
+    assert rel_close(a, np.asarray(nybb["Shape_Area"]), 2e-6)
+    t = nybb.to_arrow()
+    assert isinstance(G.from_arrow(t), G.GeoDataFrame) and isinstance(G.from_arrow(t.column("geometry")), G.GeoSeries)
+    with pytest.raises(ValueError):
+        datasets.get_path("atlantis")
+
+
 def test_affine_matrix_order_is_geos(ctx):
     """The reference binding hands the Python list to geo untouched (py-geopolars/src/geo.rs:10-13:
     `series.affine_transform(transform)` with `transform: [f64; 6]`, and geo's `From<[T; 6]>` is
