@@ -143,12 +143,23 @@ def bind_to_gpu_numa_node(local_rank: int):
     there.  Returns (node, previous affinity) or (None, previous affinity) when the topology cannot be read."""
     prev = set(all_cpus())
     try:
-        import torch
+        path = None
+        try:
+            import torch
 
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.x
-        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
-        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+            pr = torch.cuda.get_device_properties(local_rank)
+            path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+            if not os.path.exists(path):
+                path = None
+        except Exception:
+            path = None
+        if path is None:  # NVML reports the bus id as a string
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus.lower()[-12:]}/numa_node"
         with open(path) as f:
             node = int(f.read().strip())
         if node < 0:

@@ -18,6 +18,7 @@
 // for element, so even exact ties for "farthest" resolve like the restated geo code (Iterator::max_by keeps the
 // LAST maximal element of the slice).  DESIGN.md "convex_hull".
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(kHullWarps * 32, SMEM ? 5 : 2) k_hull(int type
                                                                         const int64_t *__restrict__ ring_off,
                                                                         const uint8_t *__restrict__ validity, int32_t cap,
                                                                         uint8_t *__restrict__ workspace, int64_t *__restrict__ counts,
-                                                                        const int64_t *__restrict__ out_off, double2 *__restrict__ out_xy) {
+                                                                        const int64_t *__restrict__ out_off, double2 *__restrict__ out_xy,
+                                                                        const uint8_t *__restrict__ only) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t warp_slot = (size_t)blockIdx.x * kHullWarps + wid;
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kHullWarps * 32, SMEM ? 5 : 2) k_hull(int type
     tmp = P + cap;
     const int64_t n_warps = (int64_t)gridDim.x * kHullWarps;
     for (int64_t g = (int64_t)blockIdx.x * kHullWarps + wid; g < n_geoms; g += n_warps) {
+        if (only && !only[g]) continue;  // the level-wise kernel finished this geometry
         Emitter<WRITE> em;
         em.n = 0;
         em.out = WRITE ? out_xy + out_off[g] : nullptr;
@@ -353,6 +356,247 @@ __global__ void __launch_bounds__(kHullWarps * 32, SMEM ? 5 : 2) k_hull(int type
     }
 }
 
+// ---- fast path: the same recursion, level by level -----------------------------------------------------------------
+// geo's quick_hull is a depth-first recursion over ever smaller slices; run by one warp it spends most of its ~11 k
+// instructions on slices of a handful of points (3 of 32 lanes busy) and on the warp-wide bookkeeping of each of its ~50 calls.
+// The recursion TREE, however, does not depend on the order in which the calls are made: a call hull_set(a, b, S) picks
+// far = argmax over S of orth(a,b) . (p - a) (evaluated in f64 exactly like geo) and splits S \ {far} into
+// {p : ccw(far, b, p)} and {p : ccw(a, far, p)} — functions of (a, b, S) alone.  The only place where geo's slice ORDER
+// matters is the arg-max tie rule (Iterator::max_by keeps the last maximal element of the slice as permuted by the Hoare
+// partitions).  So: process all calls of one recursion depth together (every live point carries the id of its call; the
+// warp's lanes stride over the live points, whatever call they belong to), and whenever two points with DIFFERENT
+// coordinates tie for a maximum — or anything else happens that the level-wise form does not cover (non-finite coordinates,
+// fewer than four coordinates, min == max, a point that is strictly left of both child segments, more than 128 calls alive)
+// — flag the geometry and let the order-exact kernel above redo it.  Points with EQUAL coordinates tying (the closing
+// duplicate of a ring is one in every polygon) do not matter: whichever copy is taken, the others are collinear with
+// every segment through it and are dropped by both partitions, as in geo.
+// The emission order of geo (lower chain from min towards max, max, upper chain back, min, closing copy of the first) is
+// kept as a CHAIN of vertex ids in emission order; the points of a call sit "before" the chain vertex that is the call's
+// `a`, with `b` the previous chain vertex (cyclically); a call's far point is inserted before its `a`.
+constexpr int kHullSegCap = 128;  // live calls per level (chain length); beyond it the geometry is redone by k_hull
+struct HullFastLayout {
+    // per warp, in shared memory: P0[cap] double2 | KV[cap] u64 | EA[cap] u32 | EB[cap] u32 | HI[S] u32 | LO[S] u32 | FAR[S] i32 |
+    // NI[S] i32 | CHA[S] u16 | CHB[S] u16
+    static __host__ __device__ size_t bytes(int cap) { return (size_t)cap * 32 + (size_t)kHullSegCap * 20; }
+};
+__device__ __forceinline__ unsigned long long hull_ord(double d) {  // order-preserving, > 0 for every non-NaN value
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(kHullWarps * 32, 5) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+                                                               const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
+                                                               const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
+                                                               int32_t cap, int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
+                                                               double2 *__restrict__ out_xy, uint8_t *__restrict__ redo) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *base = smem + (size_t)wid * HullFastLayout::bytes(cap);
+    double2 *P0 = reinterpret_cast<double2 *>(base);
+    unsigned long long *KV = reinterpret_cast<unsigned long long *>(base + (size_t)cap * 16);  // this level's key of every live point
+    uint32_t *EA = reinterpret_cast<uint32_t *>(base + (size_t)cap * 24), *EB = EA + cap;
+    uint32_t *HI = EB + cap, *LO = HI + kHullSegCap;
+    int32_t *FAR = reinterpret_cast<int32_t *>(LO + kHullSegCap), *NI = FAR + kHullSegCap;
+    uint16_t *CHA = reinterpret_cast<uint16_t *>(NI + kHullSegCap), *CHB = CHA + kHullSegCap;
+    const unsigned below = (1u << lane) - 1u;
+    const int64_t n_warps = (int64_t)gridDim.x * kHullWarps;
+    for (int64_t g = (int64_t)blockIdx.x * kHullWarps + wid; g < n_geoms; g += n_warps) {
+        bool flag = false;       // warp-uniform: redo this geometry with the order-exact kernel
+        int64_t n_out = 0;
+        if (bit_get(validity, g)) {
+            const int64_t n64 = exterior_count(type, g, geom_off, part_off, ring_off);
+            if (n64 < 4 || n64 > cap) {
+                flag = true;
+            } else {
+                const int32_t n = (int32_t)n64;
+                __syncwarp();
+                exterior_gather(type, g, xy, geom_off, part_off, ring_off, P0, lane);
+                __syncwarp();
+                // ---- lexicographic min / max (any instance: equal coordinates are interchangeable here), finiteness
+                int32_t mi = -1, xi = -1;
+                double2 mn = make_double2(0.0, 0.0), mx = mn;
+                bool bad = false;
+                for (int32_t i = lane; i < n; i += 32) {
+                    const double2 q = P0[i];
+                    bad = bad || !(isfinite(q.x) && isfinite(q.y));
+                    if (mi < 0 || lex_less(q, mn)) mn = q, mi = i;
+                    if (xi < 0 || lex_less(mx, q)) mx = q, xi = i;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ox = __shfl_xor_sync(0xffffffffu, mn.x, o), oy = __shfl_xor_sync(0xffffffffu, mn.y, o);
+                    const int32_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    const double2 oq = make_double2(ox, oy);
+                    if (oi >= 0 && (mi < 0 || lex_less(oq, mn) || (!lex_less(mn, oq) && oi < mi))) mn = oq, mi = oi;
+                    const double px = __shfl_xor_sync(0xffffffffu, mx.x, o), py = __shfl_xor_sync(0xffffffffu, mx.y, o);
+                    const int32_t pi = __shfl_xor_sync(0xffffffffu, xi, o);
+                    const double2 pq = make_double2(px, py);
+                    if (pi >= 0 && (xi < 0 || lex_less(mx, pq) || (!lex_less(pq, mx) && pi < xi))) mx = pq, xi = pi;
+                }
+                flag = __any_sync(0xffffffffu, bad) || (mn.x == mx.x && mn.y == mx.y);
+                int32_t m = 2, ne = 0;  // chain length, live points
+                uint32_t *E = EA, *En = EB;
+                uint16_t *CH = CHA, *CHn = CHB;
+                if (!flag) {
+                    if (lane == 0) CH[0] = (uint16_t)xi, CH[1] = (uint16_t)mi;  // emission order: [.., max, .., min]
+                    // ---- level 0: strictly right of min->max (= left of max->min) is the lower set (call 0), strictly left the upper (call 1)
+                    for (int32_t c = 0; c < n; c += 32) {
+                        const int32_t i = c + lane;
+                        int side = 0;
+                        if (i < n) {
+                            const double2 q = P0[i];
+                            const double dl = (mx.x - q.x) * (mn.y - q.y), dr = (mx.y - q.y) * (mn.x - q.x);
+                            const double det = dl - dr;
+                            if (fabs(det) > kCcwA * (fabs(dl) + fabs(dr))) side = det > 0.0 ? 1 : 2;
+                            else {
+                                const double ex = orient2d(mx.x, mx.y, mn.x, mn.y, q.x, q.y);
+                                side = ex > 0.0 ? 1 : (ex < 0.0 ? 2 : 0);
+                            }
+                        }
+                        const unsigned mk = __ballot_sync(0xffffffffu, side != 0);
+                        if (side) E[ne + __popc(mk & below)] = (uint32_t)i | ((uint32_t)(side - 1) << 16);
+                        ne += __popc(mk);
+                    }
+                    __syncwarp();
+                }
+                // ---- one iteration per recursion depth
+                while (!flag && ne > 0) {
+                    for (int32_t j = lane; j < m; j += 32) HI[j] = 0u, LO[j] = 0u;
+                    __syncwarp();
+                    // A: per call, the maximum of orth(a,b) . (p - a): high word first
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        uint32_t hi = 0u, sg = 0xffffffffu;
+                        if (e < ne) {
+                            const uint32_t w = E[e];
+                            sg = w >> 16;
+                            const double2 p = P0[w & 0xffffu], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]];
+                            const double ox = a.y - b.y, oy = b.x - a.x, dx = p.x - a.x, dy = p.y - a.y;
+                            const unsigned long long k = hull_ord(ox * dx + oy * dy);
+                            KV[e] = k;
+                            hi = (uint32_t)(k >> 32);
+                        }
+                        const uint32_t sg0 = __shfl_sync(0xffffffffu, sg, 0);
+                        if (__all_sync(0xffffffffu, sg == sg0)) {  // a whole row of one call: one atomic instead of 32 colliding ones
+                            const uint32_t r = __reduce_max_sync(0xffffffffu, hi);
+                            if (lane == 0) atomicMax(&HI[sg0], r);
+                        } else if (e < ne) {
+                            atomicMax(&HI[sg], hi);
+                        }
+                    }
+                    __syncwarp();
+                    // B: low word among the points that hold the high word
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        if (e < ne) {
+                            const uint32_t sg = E[e] >> 16;
+                            const unsigned long long k = KV[e];
+                            if ((uint32_t)(k >> 32) == HI[sg]) atomicMax(&LO[sg], (uint32_t)k);
+                        }
+                    }
+                    __syncwarp();
+                    // C: any point holding the maximum becomes the call's far point
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        if (e < ne) {
+                            const uint32_t w = E[e], sg = w >> 16;
+                            const unsigned long long k = KV[e];
+                            if ((uint32_t)(k >> 32) == HI[sg] && (uint32_t)k == LO[sg]) FAR[sg] = (int32_t)(w & 0xffffu);
+                        }
+                    }
+                    __syncwarp();
+                    // D: a different point with the same value: geo's slice order would decide — not reproduced here
+                    bool tie = false;
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        if (e < ne) {
+                            const uint32_t w = E[e], sg = w >> 16;
+                            const unsigned long long k = KV[e];
+                            if ((uint32_t)(k >> 32) == HI[sg] && (uint32_t)k == LO[sg]) {
+                                const double2 p = P0[w & 0xffffu], f = P0[FAR[sg]];
+                                tie = tie || !(p.x == f.x && p.y == f.y);
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, tie)) {
+                        flag = true;
+                        break;
+                    }
+                    // chain update: the far point of every live call goes in front of the call's `a`
+                    int32_t added = 0;
+                    for (int32_t c = 0; c < m; c += 32) {
+                        const int32_t j = c + lane;
+                        const bool live = j < m && HI[j] != 0u;
+                        const unsigned mk = __ballot_sync(0xffffffffu, live);
+                        if (j < m) {
+                            const int32_t nj = j + added + __popc(mk & below) + (live ? 1 : 0);
+                            NI[j] = nj;
+                            if (nj < kHullSegCap) CHn[nj] = CH[j];
+                            if (live && nj - 1 < kHullSegCap) CHn[nj - 1] = (uint16_t)FAR[j];
+                        }
+                        added += __popc(mk);
+                    }
+                    if (m + added > kHullSegCap) {
+                        flag = true;
+                        break;
+                    }
+                    __syncwarp();
+                    // E: every point moves to one of its call's two children, or drops out
+                    int32_t ne2 = 0;
+                    bool both = false;
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        uint32_t nw = 0u;
+                        bool keep = false;
+                        if (e < ne) {
+                            const uint32_t w = E[e], sg = w >> 16, pi = w & 0xffffu;
+                            const int32_t nj = NI[sg];
+                            const double2 p = P0[pi], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]], f = P0[CHn[nj - 1]];
+                            if (!(p.x == f.x && p.y == f.y)) {
+                                const bool t1 = is_ccw(f, b, p), t2 = is_ccw(a, f, p);
+                                both = both || (t1 && t2);
+                                keep = t1 || t2;
+                                nw = pi | ((uint32_t)(t1 ? nj - 1 : nj) << 16);
+                            }
+                        }
+                        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                        if (keep) En[ne2 + __popc(mk & below)] = nw;
+                        ne2 += __popc(mk);
+                    }
+                    if (__any_sync(0xffffffffu, both)) {
+                        flag = true;
+                        break;
+                    }
+                    __syncwarp();
+                    {
+                        uint32_t *t = E;
+                        E = En, En = t;
+                        uint16_t *u = CH;
+                        CH = CHn, CHn = u;
+                    }
+                    m += added;
+                    ne = ne2;
+                }
+                if (!flag) {  // the chain IS the ring: [.., max, .., min] (+ the closing copy of the first vertex)
+                    const double2 first = P0[CH[0]];
+                    const bool close = !(first.x == mn.x && first.y == mn.y);
+                    n_out = m + (close ? 1 : 0);
+                    if (WRITE) {
+                        double2 *dst = out_xy + out_off[g];
+                        for (int32_t j = lane; j < m; j += 32) dst[j] = P0[CH[j]];
+                        if (close && lane == 0) dst[m] = first;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            if (redo) redo[g] = flag ? 1 : 0;
+            if (counts != nullptr && !flag) counts[g] = n_out;
+        }
+        __syncwarp();
+    }
+}
+
 // upper bound of the hull ring length of geometry g: all exterior coordinates + the closing vertex
 __global__ void k_hull_upper(int type, int64_t n_geoms, const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
                              const int64_t *__restrict__ ring_off, int64_t *__restrict__ ub) {
@@ -411,15 +655,41 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
     }
     GPL_TRY(workspace.get(ctx, (stack_bytes + (use_smem ? 0 : stage_bytes)) * kHullWarps * (size_t)grid));
     const size_t dyn = use_smem ? smem_bytes : 0;
+    // The level-wise kernel takes every geometry it can (4 <= coordinates <= fast_cap, finite, no arg-max tie between distinct
+    // points); what it flags in `redo` is recomputed by the order-exact kernel.  GPL_HULL_FAST=0 runs the exact kernel alone.
+    static const bool fast_enabled = [] {
+        const char *e = getenv("GPL_HULL_FAST");
+        return !e || atoi(e) != 0;
+    }();
+    const int32_t fast_cap = (int32_t)((std::min<unsigned long long>(std::max<unsigned long long>(h_max, 4), 1024) + 1) & ~1ULL);
+    const size_t fast_smem = HullFastLayout::bytes(fast_cap) * kHullWarps;
+    int fast_grid = 1;
+    Scratch<uint8_t> redo;
+    if (fast_enabled && n > 0) {
+        GPL_TRY(redo.get(ctx, (size_t)n));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true>, kHullWarps * 32, fast_smem) != cudaSuccess || occ < 1) occ = 1;
+        (void)cudaGetLastError();
+        fast_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kHullWarps), (int64_t)kSMs * occ));
+    }
     // pass: 0 = count only, 1 = write.  `off`/`dst` are the ring offsets and the output buffer of a writing pass.
     auto launch = [&](bool write, int64_t *cnt, const int64_t *off, double2 *dst) -> int {
         if (n == 0) return GPL_OK;
+        const uint8_t *only = nullptr;
+        if (fast_enabled) {
+            if (write) k_hull_fast<true><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p);
+            else k_hull_fast<false><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p);
+            ctx->launches++;
+            only = redo.p;
+        }
         if (use_smem) {
-            if (write) k_hull<true, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
-            else k_hull<false, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+            if (write) k_hull<true, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst, only);
+            else k_hull<false, true><<<grid, kHullWarps * 32, dyn, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst, only);
         } else {
-            if (write) k_hull<true, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
-            else k_hull<false, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst);
+            if (write) k_hull<true, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst, only);
+            else k_hull<false, false><<<grid, kHullWarps * 32, 0, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, cap, workspace.p, cnt, off, dst, only);
         }
         ctx->launches++;
         GPL_CUDA(cudaGetLastError());

@@ -143,6 +143,7 @@ struct gpl_pip_index {
     bool lean_ok = false;             // every valid part is a plain POLYGON with FP32 lists: LEAN walk
     int64_t n_not_fast = 0;           // valid parts without FP32 lists
     unsigned long long *n_deferred = nullptr;  // device counters inside the slab: [0] this launch, [1] since the build
+    unsigned long long *phase_t = nullptr;     // 16 build-phase time stamps (ns), inside the slab
     uint32_t *deferred_list = nullptr;         // indices of deferred points (grown on demand)
     uint32_t deferred_cap = 0;
     int64_t bytes = 0;
@@ -227,7 +228,17 @@ struct BuildArgs {
     float4 *fast;
     uint32_t *raster;
     unsigned long long *n_deferred;
+    unsigned long long *phase_t;  // 16 global-timer stamps (ns) taken by one thread at the phase boundaries of both kernels
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GPL_STAMP(a, k)                                                              \
+    do {                                                                             \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (a).phase_t) (a).phase_t[k] = global_ns(); \
+    } while (0)
 
 __device__ __forceinline__ void part_rings(int type, int64_t part, const int64_t *geom_off, const int64_t *part_off,
                                            int64_t &r0, int64_t &r1) {
@@ -1007,6 +1018,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildAr
     __shared__ GridParams sm_g;
     const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     // S0: zero the counters the later phases add into; headers + union bbox
+    GPL_STAMP(a, 0);
     for (int64_t i = tid; i <= a.n_cells; i += nth) a.cell_count[i] = 0;
     for (int64_t i = tid; i <= a.NB_cap; i += nth) {
         a.bcount[i] = 0;
@@ -1014,6 +1026,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildAr
     }
     ph_headers(a, sm_box);
     grid.sync();
+    GPL_STAMP(a, 1);
     // S1: grid parameters (every CTA derives the same values), cell counts, chunk-local scan of the bucket counts
     if (threadIdx.x == 0) {
         sm_g = grid_from_acc(a);
@@ -1023,6 +1036,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildAr
     ph_cells<0>(a, sm_g);
     grid_scan_local(a.nb, a.nb, a.P, a.partial, sm_scan);
     grid.sync();
+    GPL_STAMP(a, 2);
     // S2: bucket bases (finishing the scan), bucket entry counts
     {
         const int64_t total = grid_scan_prefix(a.partial, sm_prefix, sm_scan);
@@ -1031,8 +1045,10 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildAr
         ph_buckets<0>(a, sm_prefix, ceil_div_dev(a.P > 0 ? a.P : 1, gridDim.x));
     }
     grid.sync();
+    GPL_STAMP(a, 3);
     // S3: FP32 table plan
     ph_fast_plan(a);
+    GPL_STAMP(a, 4);  // (one CTA's view: the kernel ends when the slowest CTA does)
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArgs a) {
@@ -1043,6 +1059,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
     const GridParams g = *a.gp;
     const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     const bool degenerate = g.inv_fw == 0.0 || g.inv_fh == 0.0;
+    GPL_STAMP(a, 5);
     // T0: chunk-local scans (in place): cell counts -> cell starts, bucket counts -> bucket starts, FP32 slots ->
     // FP32 bases; raster cleared (all 3 on a degenerate grid: every point walks)
     grid_scan_local(a.cell_count, a.cell_count, a.n_cells, a.partial, sm_scan);
@@ -1054,6 +1071,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
         for (int64_t i = tid; i < n_words; i += nth) a.raster[i] = fillv;
     }
     grid.sync();
+    GPL_STAMP(a, 6);
     // T1: add the prefixes of the chunk totals; cursors for the fill passes
     {
         int64_t total = grid_scan_prefix(a.partial, sm_prefix, sm_scan);
@@ -1078,20 +1096,26 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArg
         __syncthreads();
     }
     grid.sync();
+    GPL_STAMP(a, 7);
     const int32_t *cell_start = a.cell_count, *bstart = a.bcount;
     // T2: candidate lists of the cells, edge ids of the buckets (atomic cursors; sorted next)
     ph_cells<1>(a, g);
     ph_buckets<1>(a, nullptr, 1);
     grid.sync();
+    GPL_STAMP(a, 8);
     // T3: candidate lists in ascending order; every y-bucket finished by one thread (sort, f64 records, FP32 lists)
     ph_sort_segments<int32_t>(a.items, cell_start, a.n_cells);
     ph_bucket_finish(a, bstart);
     ph_part_recs(a);
     for (int64_t b = tid; b < a.n_buckets; b += nth) a.bucket_range[b] = make_int2(bstart[b], bstart[b + 1]);
     grid.sync();
+    GPL_STAMP(a, 9);
     // T4: cell records (need the sorted lists), raster
     ph_cell_finish(a, cell_start);
+    GPL_STAMP(a, 10);
     ph_raster(a, g, cell_start, sm_raster);
+    grid.sync();  // (only so that the last stamp sees every CTA done)
+    GPL_STAMP(a, 11);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1759,7 +1783,7 @@ constexpr int32_t kCandSmemMaxCells = 12288;  // 48 KB of candidate rows per CTA
 template <bool LEAN, bool HIST>
 static void launch_stream(const IndexView &v, const double2 *pts, const uint8_t *val, int64_t m, int32_t *first, int32_t *cnt,
                           const gpl_pip_index *idx, int vec_ok, unsigned long long *hist, int32_t n_bins, cudaStream_t stream) {
-    static const bool csm_enabled = env_int("GPL_PIP_CAND_SMEM", 1) != 0;
+    static const bool csm_enabled = env_int("GPL_PIP_CAND_SMEM", 0) != 0;  // measured slower on config 2 (0.98 vs 0.90 ms): opt-in
     const int64_t n_cells = (int64_t)v.grid.gx * v.grid.gy;
     if (!HIST && csm_enabled && n_cells <= kCandSmemMaxCells) {
         const size_t smem = sizeof(StreamSmem) + sizeof(int32_t) * (size_t)n_cells;
@@ -1948,6 +1972,18 @@ extern "C" int gpl_pip_index_stats(gpl_ctx *ctx, const gpl_pip_index *idx, int64
     return GPL_OK;
 }
 
+// build timeline of the FILL kernel (diagnostics): out12[k] = microseconds from the kernel's start to phase boundary k
+// (5 = start, 6..9 = after grid barriers T0..T3, 10 = cell records done, 11 = raster done); synchronises the stream.
+extern "C" int gpl_pip_index_phases(gpl_ctx *ctx, const gpl_pip_index *idx, double *out12) {
+    GPL_REQUIRE(ctx && idx && out12, GPL_ERR_INVALID_ARG, "gpl_pip_index_phases: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long h[16];
+    GPL_CUDA(cudaMemcpyAsync(h, idx->phase_t, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 12; ++k) out12[k] = k >= 5 ? (double)(h[k] - h[5]) * 1e-3 : 0.0;
+    return GPL_OK;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename K>
@@ -2002,7 +2038,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     if (G < 1) G = 1;
     if (G > 2048) G = 2048;
     const int64_t n_cells = G * G;
-    static const int rs_max = std::min(7, std::max(0, env_int("GPL_PIP_RASTER_LOG2", 6)));
+    static const int rs_max = std::min(7, std::max(0, env_int("GPL_PIP_RASTER_LOG2", 7)));
     static const int64_t raster_budget = (int64_t)std::max(1, env_int("GPL_PIP_RASTER_MCELLS", 64)) << 20;
     int rs = rs_max;
     while (rs > 0 && (((G << rs) > (1 << 20)) || ((G << rs) * (G << rs) > raster_budget))) --rs;
@@ -2080,6 +2116,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     const size_t o_brange = carve(sizeof(int2) * (idx->n_buckets + 1));
     const size_t o_items = carve(sizeof(int32_t) * (idx->n_overflow + 1));
     const size_t o_defer = carve(2 * sizeof(unsigned long long));
+    const size_t o_phase = carve(16 * sizeof(unsigned long long));
     const bool all_fast = idx->n_fast > 0 && !idx->multi && !idx->any_holes;
     {
         static const bool lean_enabled = env_int("GPL_PIP_LEAN", 1) != 0;  // GPL_PIP_LEAN=0 forces the full walk (A/B measurements)
@@ -2103,6 +2140,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     idx->cell_overflow = (int32_t *)(idx->slab + o_items);
     idx->entry_ring = idx->any_holes ? (int32_t *)(idx->slab + o_ring) : nullptr;
     idx->n_deferred = (unsigned long long *)(idx->slab + o_defer);
+    idx->phase_t = (unsigned long long *)(idx->slab + o_phase);
     idx->fast = (float4 *)(idx->slab + o_fast);
     idx->bytes = (int64_t)off;
 
@@ -2114,7 +2152,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     a.cell_cursor = cell_cursor.p, a.bcursor = bcursor.p, a.entry_edge = entry_edge.p;
     a.cells = idx->cells, a.cand01 = idx->cand01, a.items = idx->cell_overflow, a.parts = idx->parts;
     a.bucket_range = idx->bucket_range, a.entries = idx->entries, a.entry_ring = idx->entry_ring, a.fast = idx->fast;
-    a.raster = idx->raster, a.n_deferred = idx->n_deferred;
+    a.raster = idx->raster, a.n_deferred = idx->n_deferred, a.phase_t = idx->phase_t;
     CUDAF(cudaMemsetAsync(idx->n_deferred, 0, 2 * sizeof(unsigned long long), st));
     {
         void *args[] = {&a};

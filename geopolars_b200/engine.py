@@ -501,6 +501,12 @@ class PipIndex:
                 "bytes", "coarse_cells_per_axis")
         return dict(zip(keys, (int(v) for v in out)))
 
+    def phases(self):
+        """microseconds from the start of the index fill kernel to its phase boundaries (diagnostics)"""
+        out = np.zeros(12, dtype=np.float64)
+        check(self.ctx.lib.gpl_pip_index_phases(self.ctx._h, self._h, _np_ptr(out)))
+        return out[5:].tolist()
+
     def query(self, points_xy: np.ndarray, with_count: bool = False):
         """first containing polygon row per point (-1 = none) [+ number of containing rows]."""
         pts = np.ascontiguousarray(points_xy, dtype=np.float64).reshape(-1, 2)

@@ -246,6 +246,8 @@ int64_t gpl_pip_index_bytes(const gpl_pip_index *idx);
  * [3] = raster cells coded "walk", [4] = raster cells coded "inside", [5] = parts without FP32 lists,
  * [6] = index bytes, [7] = coarse cells per axis. */
 int gpl_pip_index_stats(gpl_ctx *ctx, const gpl_pip_index *idx, int64_t *out8);
+/* diagnostics: microseconds from the start of the index fill kernel to each of its phase boundaries (out12[5..11]) */
+int gpl_pip_index_phases(gpl_ctx *ctx, const gpl_pip_index *idx, double *out12);
 /* spatial_join(points, polygons, Inner) candidate+exact test (spatial_index.rs:74-143):
  * first_id[p] = lowest polygon row containing point p, or -1; count[p] (may be NULL) = number of
  * containing rows.  points: xy interleaved, n points, in `mem`. */

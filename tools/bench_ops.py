@@ -38,7 +38,7 @@ def timed(stream, fn, reps=5, warm=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the BASELINE sizes")
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_ops_roofline.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_ops_roofline.json"))
     args = ap.parse_args()
     peak = 6569.3
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -55,6 +55,7 @@ with torch.cuda.stream(st):
         builds.append(1e3 * (time.perf_counter() - t0))
     builds = builds[2:]
     stats = idx.stats()
+    phases = idx.phases()
     q = []
     for _ in range(args.reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -79,6 +80,7 @@ with torch.cuda.stream(st):
         "hit_rate": hits / n, "checksum": checksum, "index_MB": stats["bytes"] / 1e6,
         "raster_log2": stats["raster_log2"], "fine_cells_per_axis": fg,
         "walk_cell_frac": stats["raster_walk_cells"] / max(1, fg * fg), "inside_cell_frac": stats["raster_inside_cells"] / max(1, fg * fg),
+        "fill_phases_us": [round(v, 1) for v in phases],
         "deferred_per_query": stats["deferred"] / (args.reps + 2), "parts_not_fast": stats["parts_not_fast"],
     }
     print(json.dumps(line), flush=True)

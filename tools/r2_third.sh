@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 T=r2c
-timeout 1200 python -m pytest tests/test_gpu_pip.py tests/test_gpu_join.py tests/test_gpu_predicates.py tests/test_gpu_ops.py tests/test_gpu_geodesic.py -x -q > gpurun_out/${T}_pytest_a.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_a.log
+timeout 1200 python -m pytest tests/test_gpu_pip.py tests/test_gpu_join.py tests/test_gpu_hull.py tests/test_gpu_predicates.py tests/test_gpu_ops.py tests/test_gpu_geodesic.py tests/test_gpu_formats.py -x -q > gpurun_out/${T}_pytest_a.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_a.log
 tail -15 gpurun_out/${T}_pytest_a.log
 rm -f gpurun_out/${T}_exp.jsonl
 for cfg in "GPL_PIP_RASTER_LOG2=6" "GPL_PIP_RASTER_LOG2=6 GPL_PIP_CAND_SMEM=0" "GPL_PIP_RASTER_LOG2=5" "GPL_PIP_RASTER_LOG2=6 GPL_L2_PIN=0"; do
