@@ -595,7 +595,7 @@ __device__ void ph_fast_plan(const BuildArgs &a) {
         if (not_fast) atomicAdd(a.acc + ACC_NOT_FAST, not_fast);
     }
 }
-// One THREAD per y-bucket finishes it: sorts the bucket's edge ids (ascending => grouped by ring, deterministic),
+// One THREAD per y-bucket finishes it: orders the bucket's edge ids where a consumer needs it (parts with holes),
 // materialises the 32-byte f64 records (+ ring index when holes exist) and writes the bucket's two FP32 lists (header, float
 // edges relative to the part origin, sentinels, overflow records).  Round 2's first build did these as three warp-per-part
 // phases separated by grid barriers; a part's ~22 buckets then cost ~44 dependent L2 round trips per warp.  Here every
@@ -604,28 +604,16 @@ __device__ void ph_bucket_finish(const BuildArgs &a, const int32_t *__restrict__
     const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     const float inf = __int_as_float(0x7f800000);
     const float4 sentinel = make_float4(0.0f, inf, 0.0f, inf);  // inert: +inf ordinates never straddle a finite p.y
-    constexpr int kLocal = 32;
     for (int64_t gb = tid; gb < a.n_buckets; gb += nth) {
         const int32_t e0 = bstart[gb], n = bstart[gb + 1] - e0;
         const int32_t p = a.bucket_part[gb];
         const PartHeader h = a.hdr[p];
         int64_t r0, r1;
         part_rings(a.type, p, a.geom_off, a.part_off, r0, r1);
-        // ---- sort the edge ids
-        int64_t loc[kLocal];
-        const bool local = n <= kLocal;
-        if (local) {
-            for (int32_t i = 0; i < n; ++i) loc[i] = a.entry_edge[e0 + i];
-            for (int32_t i = 1; i < n; ++i) {
-                const int64_t v = loc[i];
-                int32_t j = i - 1;
-                while (j >= 0 && loc[j] > v) {
-                    loc[j + 1] = loc[j];
-                    --j;
-                }
-                loc[j + 1] = v;
-            }
-        } else {
+        // ---- order: parts WITH holes need their entries grouped by ring (ascending edge id does it: the bucket walk switches
+        // ring when the ring index changes).  For a hole-free part the order in which the atomic cursors filled the bucket is
+        // irrelevant to every consumer (winding sums and the two one-sided lists are order-independent), so it is kept.
+        if (h.flags & 1) {
             int64_t *g = a.entry_edge + e0;
             for (int32_t i = 1; i < n; ++i) {
                 const int64_t v = g[i];
@@ -651,13 +639,16 @@ __device__ void ph_bucket_finish(const BuildArgs &a, const int32_t *__restrict__
             xm = fast_split_x(h);  // == 0.5 * (ox + mx); the query kernel forms it from PartLite
         }
         int32_t c0 = 0, c1 = 0;  // lengths of the two one-sided lists
+        const int64_t ext0 = a.ring_off[r0], ext1 = a.ring_off[r0 + 1];
         for (int32_t k = 0; k < n; ++k) {
-            const int64_t c = local ? loc[k] : a.entry_edge[e0 + k];
-            // ring of coordinate c: rings of a part are few; linear search from the exterior
-            int64_t r = r0;
-            while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
+            const int64_t c = a.entry_edge[e0 + k];
+            int64_t r = r0, rc0 = ext0, rc1 = ext1;
+            if (h.flags & 1) {  // ring of coordinate c: rings of a part are few; linear search from the exterior
+                while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
+                rc0 = a.ring_off[r], rc1 = a.ring_off[r + 1];
+            }
             double2 s, e;
-            edge_of_slot(a.xy, c, a.ring_off[r], a.ring_off[r + 1], s, e);
+            edge_of_slot(a.xy, c, rc0, rc1, s, e);
             EdgeRec rec;
             rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
             a.entries[e0 + k] = rec;
@@ -829,21 +820,19 @@ __device__ __forceinline__ void raster_or_span(uint32_t *__restrict__ raster, in
         atomicOr(row + w, rep & m);
     }
 }
-// One row of raster_mark: mark (code 3) every fine cell of row r within 1e-6 cells of the segment whose images in cell
-// units are (tsx,tsy)-(tex,tey).
+// One row of the marking: code 3 for every fine cell of row r within 1e-6 cells of the segment whose images in cell units
+// are (tsx,tsy)-(tex,tey).  inv_dy = 1 / (tey - tsy), or 0 for a segment that is nearly horizontal in cell units.
 __device__ __forceinline__ void raster_mark_row(uint32_t *__restrict__ raster, const GridParams &g, int32_t r, double tsx, double tsy,
-                                                double tex, double tey) {
+                                                double tex, double tey, double inv_dy) {
     const double eps = 1e-6;
-    const double dy = tey - tsy, dx = tex - tsx;
     double xa, xb;
-    if (fabs(dy) < 1e-3) {  // nearly horizontal in cell units: the whole x-range on each of the (at most 3) rows
+    if (inv_dy == 0.0) {  // |dy| < 1e-3 cells: the whole x-range on each of the (at most 3) rows
         xa = fmin(tsx, tex), xb = fmax(tsx, tex);
     } else {
         // parameter range of the segment inside the slab [r - eps, r + 1 + eps].  Errors: the endpoints are within
         // 2^-30 of their true images and so is dy, i.e. lambda is off by at most 4 * 2^-30 / |dy| — 270 times
         // smaller than the eps / |dy| the slab was widened by; x(lambda) adds a few 2^-32.  The 2e-6 margin below
-        // covers the rest.
-        const double inv_dy = 1.0 / dy;
+        // covers the rest (and the 2^-52 relative error of multiplying by the reciprocal instead of dividing).
         double l0 = ((double)r - eps - tsy) * inv_dy, l1 = ((double)r + 1.0 + eps - tsy) * inv_dy;
         if (l0 > l1) {
             const double t = l0;
@@ -851,6 +840,7 @@ __device__ __forceinline__ void raster_mark_row(uint32_t *__restrict__ raster, c
         }
         l0 = fmax(l0, 0.0), l1 = fmin(l1, 1.0);
         if (l0 > l1) return;  // a clamped border row the segment does not reach (no query point maps there)
+        const double dx = tex - tsx;
         xa = tsx + l0 * dx, xb = tsx + l1 * dx;
         if (xa > xb) {
             const double t = xa;
@@ -896,6 +886,7 @@ __device__ __forceinline__ void raster_fill_span(const BuildArgs &a, const GridP
 constexpr int kRowCross = 24;  // a horizontal line through a config-2 star crosses 12-17 edges
 constexpr int kRowStride = kRowCross + 1;  // odd stride: the 32 lists of a chunk do not collide on banks
 struct RasterSmem {
+    double ry[kBuildThreads / 32][32];  // centre-line ordinate of every row of the chunk (one division per row, not per edge)
     int32_t cnt[kBuildThreads / 32][32];
     uint32_t list[kBuildThreads / 32][32 * kRowStride];  // cell (20 bits) | down (bit 20) | ring (bits 21..31, saturated)
 };
@@ -906,6 +897,7 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
     if (g.inv_fw == 0.0 || g.inv_fh == 0.0) return;  // degenerate axis: the raster was filled with 3 (fill kernel, T0)
     int32_t *cnt = sm.cnt[wid];
     uint32_t *list = sm.list[wid];
+    double *row_y = sm.ry[wid];
     for (int64_t p = warp; p < a.P; p += nwarps) {
         const PartHeader h = a.hdr[p];
         if (!(h.flags & 2)) continue;
@@ -917,6 +909,7 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
         for (int32_t ra = fy0; ra <= fy1; ra += 32) {
             const int32_t rb = min(ra + 31, fy1);
             cnt[lane] = 0;
+            row_y[lane] = g.y0 + ((double)(ra + lane) + 0.5) / g.inv_fh;
             __syncwarp();
             // ---- edge-major: marks + centre-line crossings of the rows [ra, rb]
             for (int64_t r = r0; r < r1; ++r) {
@@ -938,15 +931,18 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
                     const double ylo = fmin(tsy, tey), yhi = fmax(tsy, tey);
                     const int32_t er0 = max(min(max(__double2int_rd(ylo - 1e-6), 0), g.fgy - 1), ra);
                     const int32_t er1 = min(min(max(__double2int_rd(yhi + 1e-6), 0), g.fgy - 1), rb);
+                    const double tdy = tey - tsy, tdx = tex - tsx;
+                    const double inv_dy = fabs(tdy) < 1e-3 ? 0.0 : 1.0 / tdy;  // one division per edge and chunk
                     for (int32_t row = er0; row <= er1; ++row) {
-                        raster_mark_row(a.raster, g, row, tsx, tsy, tex, tey);
-                        const double ry = g.y0 + ((double)row + 0.5) / g.inv_fh;
+                        raster_mark_row(a.raster, g, row, tsx, tsy, tex, tey, inv_dy);
+                        const double ry = row_y[row - ra];
                         const bool up = s.y <= ry && e.y > ry, down = s.y > ry && e.y <= ry;
                         if (up || down) {
-                            const double tdy = tey - tsy, try_ = (ry - g.y0) * g.inv_fh;
-                            double lam = tdy != 0.0 ? (try_ - tsy) / tdy : 0.0;
+                            // crossing with the centre line, in cell units: its ordinate there is row + 1/2 up to 2^-31; only the
+                            // cell is used, and any lambda inside the slab lands in the run of cells this edge marks on this row
+                            double lam = inv_dy != 0.0 ? ((double)row + 0.5 - tsy) * inv_dy : 0.5;
                             lam = fmin(fmax(lam, 0.0), 1.0);
-                            const int32_t cj = min(max(__double2int_rd(tsx + lam * (tex - tsx)), 0), g.fgx - 1);
+                            const int32_t cj = min(max(__double2int_rd(tsx + lam * tdx), 0), g.fgx - 1);
                             const int32_t slot = atomicAdd(&cnt[row - ra], 1);
                             if (slot < kRowCross) list[(row - ra) * kRowStride + slot] = (uint32_t)cj | (down ? (1u << 20) : 0u) | ring_tag;
                         }
@@ -958,7 +954,7 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
             const int32_t fy = ra + lane;
             if (fy <= rb) {
                 const int32_t n = cnt[lane];
-                const double ry = g.y0 + ((double)fy + 0.5) / g.inv_fh;
+                const double ry = row_y[lane];
                 uint32_t *L = list + lane * kRowStride;
                 if (n > kRowCross || fine_index(ry, g.y0, g.inv_fh, g.fgy) != fy) {
                     raster_or_span(a.raster, g.wpr, fy, fx0, fx1, 3u);  // cannot be classified from the list: walk

@@ -137,8 +137,12 @@ def test_linestring_contains_point(ctx, og, conv):
 
 def test_contains_rejects_unsupported_pairs(ctx):
     a = ctx.upload(GeoArrowArray.from_shapes(T["polygon"], [[[(0, 0), (1, 0), (1, 1), (0, 0)]]]))
+    assert engine.contains(a, a).tolist() == [True]  # Polygon contains Polygon: geo's relate semantics (test_gpu_join.py)
+    ls = ctx.upload(GeoArrowArray.from_shapes(T["linestring"], [[(0, 0), (1, 1)]]))
     with pytest.raises(MismatchedGeometry):
-        engine.contains(a, a)  # Polygon contains Polygon is relate-based in geo: not on this path
+        engine.contains(a, ls)  # not a pair the reference's join dispatches (spatial_index.rs:89-137)
+    with pytest.raises(MismatchedGeometry):
+        engine.contains(ls, a)
 
 
 @pytest.mark.parametrize("ka,kb", [("linestring", "polygon"), ("polygon", "linestring"), ("polygon", "polygon")])
