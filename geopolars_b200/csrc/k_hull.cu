@@ -383,8 +383,8 @@ __device__ __forceinline__ unsigned long long hull_ord(double d) {  // order-pre
     const unsigned long long b = (unsigned long long)__double_as_longlong(d);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
-template <bool WRITE>
-__global__ void __launch_bounds__(kHullWarps * 32, 5) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+template <bool WRITE, int MINB>
+__global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
                                                                const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
                                                                const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
                                                                int32_t cap, int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
@@ -661,16 +661,25 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         const char *e = getenv("GPL_HULL_FAST");
         return !e || atoi(e) != 0;
     }();
+    // resident CTAs per SM the level-wise kernel is compiled for: 5 (96 registers, a few spills) or 4 (128 registers)
+    static const int fast_minb = [] {
+        const char *e = getenv("GPL_HULL_MINB");
+        return e ? atoi(e) : 5;
+    }();
     const int32_t fast_cap = (int32_t)((std::min<unsigned long long>(std::max<unsigned long long>(h_max, 4), 1024) + 1) & ~1ULL);
     const size_t fast_smem = HullFastLayout::bytes(fast_cap) * kHullWarps;
     int fast_grid = 1;
     Scratch<uint8_t> redo;
     if (fast_enabled && n > 0) {
         GPL_TRY(redo.get(ctx, (size_t)n));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
         int occ = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true>, kHullWarps * 32, fast_smem) != cudaSuccess || occ < 1) occ = 1;
+        const cudaError_t oe = fast_minb >= 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true, 5>, kHullWarps * 32, fast_smem)
+                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true, 4>, kHullWarps * 32, fast_smem);
+        if (oe != cudaSuccess || occ < 1) occ = 1;
         (void)cudaGetLastError();
         fast_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kHullWarps), (int64_t)kSMs * occ));
     }
@@ -679,8 +688,15 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         if (n == 0) return GPL_OK;
         const uint8_t *only = nullptr;
         if (fast_enabled) {
-            if (write) k_hull_fast<true><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p);
-            else k_hull_fast<false><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p);
+#define GPL_HULL_FAST_LAUNCH(W, B) k_hull_fast<W, B><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p)
+            if (fast_minb >= 5) {
+                if (write) GPL_HULL_FAST_LAUNCH(true, 5);
+                else GPL_HULL_FAST_LAUNCH(false, 5);
+            } else {
+                if (write) GPL_HULL_FAST_LAUNCH(true, 4);
+                else GPL_HULL_FAST_LAUNCH(false, 4);
+            }
+#undef GPL_HULL_FAST_LAUNCH
             ctx->launches++;
             only = redo.p;
         }

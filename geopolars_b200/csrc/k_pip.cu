@@ -640,33 +640,51 @@ __device__ void ph_bucket_finish(const BuildArgs &a, const int32_t *__restrict__
         }
         int32_t c0 = 0, c1 = 0;  // lengths of the two one-sided lists
         const int64_t ext0 = a.ring_off[r0], ext1 = a.ring_off[r0 + 1];
-        for (int32_t k = 0; k < n; ++k) {
-            const int64_t c = a.entry_edge[e0 + k];
-            int64_t r = r0, rc0 = ext0, rc1 = ext1;
-            if (h.flags & 1) {  // ring of coordinate c: rings of a part are few; linear search from the exterior
-                while (r + 1 < r1 && a.ring_off[r + 1] <= c) ++r;
-                rc0 = a.ring_off[r], rc1 = a.ring_off[r + 1];
-            }
-            double2 s, e;
-            edge_of_slot(a.xy, c, rc0, rc1, s, e);
-            EdgeRec rec;
-            rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
-            a.entries[e0 + k] = rec;
-            if (a.entry_ring) a.entry_ring[e0 + k] = (int32_t)(r - r0);
-            if (fast) {
-                if (fmax(s.x, e.x) >= xm) {  // right-hand list: coordinates relative to (xminf, yminf)
-                    const float4 f = make_float4(__double2float_rn(s.x - ox), __double2float_rn(s.y - oy), __double2float_rn(e.x - ox),
-                                                 __double2float_rn(e.y - oy));
-                    if (c0 < kFastListRecs - 1) list0[1 + c0] = f;
-                    else base[ovf.x + c0 - (kFastListRecs - 1)] = f;
-                    ++c0;
+        // four entries at a time: their edge ids, then their coordinates, are loaded together (read-only path) before
+        // anything is stored — one entry per iteration cost two dependent L2 round trips each
+        for (int32_t k0 = 0; k0 < n; k0 += 4) {
+            const int32_t mm = min(4, n - k0);
+            int64_t cc[4], rr[4];
+            double2 ss[4], ee[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cc[j] = j < mm ? __ldg(a.entry_edge + e0 + k0 + j) : ext0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int64_t r = r0, rc0 = ext0, rc1 = ext1;
+                if (h.flags & 1) {  // ring of coordinate c: rings of a part are few; linear search from the exterior
+                    while (r + 1 < r1 && a.ring_off[r + 1] <= cc[j]) ++r;
+                    rc0 = a.ring_off[r], rc1 = a.ring_off[r + 1];
                 }
-                if (fmin(s.x, e.x) <= xm) {  // left-hand list, mirrored in x
-                    const float4 f = make_float4(__double2float_rn(mx - s.x), __double2float_rn(s.y - oy), __double2float_rn(mx - e.x),
-                                                 __double2float_rn(e.y - oy));
-                    if (c1 < kFastListRecs - 1) list1[1 + c1] = f;
-                    else base[ovf.y + c1 - (kFastListRecs - 1)] = f;
-                    ++c1;
+                rr[j] = r - r0;
+                // edge_of_slot on the read-only path: (c -> c+1), or the closing edge back to the ring's first coordinate,
+                // or the degenerate edge of a 1-coordinate ring (entries never name a "no edge" slot)
+                ss[j] = __ldg(a.xy + cc[j]);
+                ee[j] = cc[j] + 1 < rc1 ? __ldg(a.xy + cc[j] + 1) : (rc1 - rc0 == 1 ? ss[j] : __ldg(a.xy + rc0));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= mm) break;
+                const double2 s = ss[j], e = ee[j];
+                const int32_t k = k0 + j;
+                EdgeRec rec;
+                rec.sx = s.x, rec.sy = s.y, rec.ex = e.x, rec.ey = e.y;
+                a.entries[e0 + k] = rec;
+                if (a.entry_ring) a.entry_ring[e0 + k] = (int32_t)rr[j];
+                if (fast) {
+                    if (fmax(s.x, e.x) >= xm) {  // right-hand list: coordinates relative to (xminf, yminf)
+                        const float4 f = make_float4(__double2float_rn(s.x - ox), __double2float_rn(s.y - oy), __double2float_rn(e.x - ox),
+                                                     __double2float_rn(e.y - oy));
+                        if (c0 < kFastListRecs - 1) list0[1 + c0] = f;
+                        else base[ovf.x + c0 - (kFastListRecs - 1)] = f;
+                        ++c0;
+                    }
+                    if (fmin(s.x, e.x) <= xm) {  // left-hand list, mirrored in x
+                        const float4 f = make_float4(__double2float_rn(mx - s.x), __double2float_rn(s.y - oy), __double2float_rn(mx - e.x),
+                                                     __double2float_rn(e.y - oy));
+                        if (c1 < kFastListRecs - 1) list1[1 + c1] = f;
+                        else base[ovf.y + c1 - (kFastListRecs - 1)] = f;
+                        ++c1;
+                    }
                 }
             }
         }
@@ -1047,7 +1065,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_pip_build_count(const BuildAr
     GPL_STAMP(a, 4);  // (one CTA's view: the kernel ends when the slowest CTA does)
 }
 
-__global__ void __launch_bounds__(kBuildThreads) k_pip_build_fill(const BuildArgs a) {
+__global__ void __launch_bounds__(kBuildThreads, 3) k_pip_build_fill(const BuildArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int64_t sm_scan[kBuildThreads / 32 + 1];
     __shared__ int64_t sm_prefix[kMaxBuildCtas];

@@ -1,0 +1,22 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+T=r2f
+timeout 900 python -m pytest tests/test_gpu_pip.py tests/test_gpu_hull.py -q > gpurun_out/${T}_pytest_a.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_a.log
+tail -4 gpurun_out/${T}_pytest_a.log
+rm -f gpurun_out/${T}_exp.jsonl
+for cfg in "GPL_PIP_RASTER_LOG2=6"; do
+  env $cfg timeout 300 python tools/exp_pip2.py --reps 3 --tag "$cfg" >> gpurun_out/${T}_exp.jsonl 2>> gpurun_out/${T}_exp.err
+done
+cat gpurun_out/${T}_exp.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['tag'],'| build',round(d['build_ms_min'],3),'| query',round(d['query_ms_min'],3),'| chk',d['checksum'],'| phases us',d['fill_phases_us'])
+"
+for cfg in "GPL_HULL_MINB=5" "GPL_HULL_MINB=4"; do
+  echo "== $cfg"; env $cfg timeout 600 python bench.py --workload c5 --points 3000000 --steps 3 --warmup 3 --no-e2e --no-cpu 2> gpurun_out/${T}_c5_$cfg.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('c5 3M polys: ms/step',round(d['ms_per_step'],2))"
+done
+timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; python -c "
+import json; d=json.load(open('gpurun_out/${T}_bench_c2.json')); print('c2 value %.3g ms/step %.3f kernel %.3f frac %.3f'%(d['value'],d['ms_per_step'],d['config']['kernel_ms'],d['roofline']['frac']))"
