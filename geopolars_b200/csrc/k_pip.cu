@@ -130,7 +130,7 @@ struct gpl_pip_index {
     gpl::PartRec *parts = nullptr;
     gpl::CellRec *cells = nullptr;    // gx*gy
     int2 *cand01 = nullptr;           // gx*gy: polygon ROW of the cell's candidate #0 / #1 (-1 = none): raster codes 1 / 2
-    uint32_t *raster = nullptr;       // fgy rows x wpr words, 2 bits per fine cell
+    uint2 *raster = nullptr;          // fgy rows x wpr words: x = 2 bits per fine cell (16 cells), y = row of the coarse cell's candidate #0
     int32_t *cell_overflow = nullptr; // ascending part ids of the cells' candidates
     int2 *bucket_range = nullptr;     // n_buckets: (start, end) into entries[]
     gpl::EdgeRec *entries = nullptr;
@@ -226,7 +226,7 @@ struct BuildArgs {
     EdgeRec *entries;
     int32_t *entry_ring;
     float4 *fast;
-    uint32_t *raster;
+    uint2 *raster;          // per 16 fine cells: x = their 2-bit codes, y = the row of the coarse cell's candidate #0
     unsigned long long *n_deferred;
     unsigned long long *phase_t;  // 16 global-timer stamps (ns) taken by one thread at the phase boundaries of both kernels
 };
@@ -745,6 +745,18 @@ __device__ void ph_cell_finish(const BuildArgs &a, const int32_t *__restrict__ c
         a.cand01[c] = cand;
     }
 }
+// the row of candidate #0 next to the codes it qualifies: raster code 1 (36 % of config 2's points) then needs no second
+// gather.  A word (16 fine cells) lies inside one coarse cell when 2^rs >= 16; otherwise the word keeps -2 = "ask cand01".
+__device__ void ph_raster_cand(const BuildArgs &a, const GridParams &g) {
+    const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
+    const int64_t n_words = (int64_t)g.fgy * g.wpr;
+    for (int64_t i = tid; i < n_words; i += nth) {
+        const int32_t fy = (int32_t)(i / g.wpr), wx = (int32_t)(i - (int64_t)fy * g.wpr);
+        uint32_t v = 0xfffffffeu;
+        if (g.rs >= 4) v = (uint32_t)a.cand01[(int64_t)(fy >> g.rs) * g.gx + ((wx << 4) >> g.rs)].x;
+        a.raster[i].y = v;
+    }
+}
 __device__ void ph_part_recs(const BuildArgs &a) {
     const int64_t tid = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x, nth = (int64_t)gridDim.x * kBuildThreads;
     for (int64_t p = tid; p < a.P; p += nth) {
@@ -828,19 +840,19 @@ static __device__ __noinline__ bool bucket_contains_exact(const EdgeRec *__restr
 // evaluation of geo's rule at one representative double that maps to the cell classifies every query point that maps
 // to it.  Anything this argument does not cover (degenerate axis, a representative that does not map back, non-finite
 // coordinates, more than two containing candidates) is coded 3.
-__device__ __forceinline__ void raster_or_span(uint32_t *__restrict__ raster, int32_t wpr, int32_t fy, int32_t c0, int32_t c1,
+__device__ __forceinline__ void raster_or_span(uint2 *__restrict__ raster, int32_t wpr, int32_t fy, int32_t c0, int32_t c1,
                                                uint32_t code) {
-    uint32_t *row = raster + (int64_t)fy * wpr;
+    uint2 *row = raster + (int64_t)fy * wpr;
     const uint32_t rep = code * 0x55555555u;
     for (int32_t w = c0 >> 4; w <= (c1 >> 4); ++w) {
         const int32_t lo = max(c0 - (w << 4), 0), hi = min(c1 - (w << 4), 15);  // inclusive cell range inside word w
         const uint32_t m = (0xffffffffu >> (2 * (15 - hi))) & (0xffffffffu << (2 * lo));
-        atomicOr(row + w, rep & m);
+        atomicOr(&row[w].x, rep & m);
     }
 }
 // One row of the marking: code 3 for every fine cell of row r within 1e-6 cells of the segment whose images in cell units
 // are (tsx,tsy)-(tex,tey).  inv_dy = 1 / (tey - tsy), or 0 for a segment that is nearly horizontal in cell units.
-__device__ __forceinline__ void raster_mark_row(uint32_t *__restrict__ raster, const GridParams &g, int32_t r, double tsx, double tsy,
+__device__ __forceinline__ void raster_mark_row(uint2 *__restrict__ raster, const GridParams &g, int32_t r, double tsx, double tsy,
                                                 double tex, double tey, double inv_dy) {
     const double eps = 1e-6;
     double xa, xb;
@@ -1082,7 +1094,7 @@ __global__ void __launch_bounds__(kBuildThreads, 3) k_pip_build_fill(const Build
     {
         const int64_t n_words = (int64_t)g.fgy * g.wpr;
         const uint32_t fillv = degenerate ? 0xffffffffu : 0u;
-        for (int64_t i = tid; i < n_words; i += nth) a.raster[i] = fillv;
+        for (int64_t i = tid; i < n_words; i += nth) a.raster[i] = make_uint2(fillv, 0xffffffffu);  // y: set by ph_cell_finish
     }
     grid.sync();
     GPL_STAMP(a, 6);
@@ -1128,8 +1140,10 @@ __global__ void __launch_bounds__(kBuildThreads, 3) k_pip_build_fill(const Build
     ph_cell_finish(a, cell_start);
     GPL_STAMP(a, 10);
     ph_raster(a, g, cell_start, sm_raster);
-    grid.sync();  // (only so that the last stamp sees every CTA done)
+    grid.sync();
     GPL_STAMP(a, 11);
+    // T5: candidate #0 rows beside the raster codes (needs every cell record)
+    ph_raster_cand(a, g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1143,7 +1157,7 @@ struct IndexView {
     const EdgeRec *entries;
     const int32_t *entry_ring;
     const float4 *fast;
-    const uint32_t *raster;
+    const uint2 *raster;
     const int2 *cand01;
     int32_t multi;  // polygon side is MULTIPOLYGON: several parts may share a row
     GridParams grid;
@@ -1597,7 +1611,7 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
         const int64_t base = tile * kTilePts;
         // stage 1: fine cells and raster words
         int32_t fx[4], fy[4];
-        uint32_t word[4];
+        uint2 word[4];
         bool ok[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -1606,18 +1620,20 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
             if (i >= n_pts) ok[k] = false;
             if (ok[k] && pts_validity) ok[k] = bit_get(pts_validity, i);
             fx[k] = fine_index(p[k].x, g.x0, g.inv_fw, g.fgx), fy[k] = fine_index(p[k].y, g.y0, g.inv_fh, g.fgy);
-            word[k] = ok[k] ? __ldg(ix.raster + (int64_t)fy[k] * g.wpr + (fx[k] >> 4)) : 0u;
+            word[k] = ok[k] ? __ldg(ix.raster + (int64_t)fy[k] * g.wpr + (fx[k] >> 4)) : make_uint2(0u, 0u);
         }
         // stage 2: codes -> ids
         int32_t id[4];
         uint32_t code[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            code[k] = (word[k] >> ((fx[k] & 15) * 2)) & 3u;
+            code[k] = (word[k].x >> ((fx[k] & 15) * 2)) & 3u;
             id[k] = -1;
             if (code[k] == 1u || code[k] == 2u) {
                 const int64_t cc = (int64_t)(fy[k] >> g.rs) * g.gx + (fx[k] >> g.rs);
-                if (CSM && code[k] == 1u) {
+                if (code[k] == 1u && word[k].y != 0xfffffffeu) {
+                    id[k] = (int32_t)word[k].y;  // the candidate's row travels with the codes: no second gather
+                } else if (CSM && code[k] == 1u) {
                     id[k] = cand0[cc];
                 } else {
                     const int2 cand = __ldg(ix.cand01 + cc);
@@ -1942,10 +1958,10 @@ extern "C" int64_t gpl_pip_index_bytes(const gpl_pip_index *idx) { return idx ? 
 // out[4] = raster cells coded 1 or 2, out[5] = parts without FP32 lists, out[6] = index bytes, out[7] = coarse cells per axis.
 // Synchronises the context stream.
 namespace gpl {
-__global__ void k_raster_stats(const uint32_t *__restrict__ raster, int64_t n_words, unsigned long long *__restrict__ out) {
+__global__ void k_raster_stats(const uint2 *__restrict__ raster, int64_t n_words, unsigned long long *__restrict__ out) {
     unsigned long long walk = 0, inside = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t w = raster[i], lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+        const uint32_t w = raster[i].x, lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
         walk += __popc(lo & hi);
         inside += __popc(lo ^ hi);
     }
@@ -2039,11 +2055,12 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     cudaStream_t st = ctx->stream;
     static const int grid_count = coop_grid(k_pip_build_count), grid_fill = coop_grid(k_pip_build_fill);
 
-    // edge slots per y-bucket x 100.  Measured on config 2 (B200, round-1 kernel ms): 133: 2.18, 200: 2.03, 300: 1.95,
-    // 400: 1.98, 500: 2.07 — fewer, longer buckets keep the FP32 table (and the cell grid) inside L2.
+    // edge slots per y-bucket x 100.  Round 1 (every point walks; kernel ms): 133: 2.18, 200: 2.03, 300: 1.95, 400: 1.98,
+    // 500: 2.07.  Round 2 (12 % of the points walk): 300: query 0.837 / build 0.54 ms, 600: query 0.842 / build 0.42 ms —
+    // half as many buckets to finish, the same query time.
     static const int slots_x100 = [] {
-        const int v = env_int("GPL_PIP_SLOTS_X100", 300);
-        return v >= 25 && v <= 6400 ? v : 300;
+        const int v = env_int("GPL_PIP_SLOTS_X100", 600);
+        return v >= 25 && v <= 6400 ? v : 600;
     }();
     // coarse grid: about one cell per part.  Fine grid: 2^rs x 2^rs cells per coarse cell, as fine as a budget of
     // raster cells allows (2 bits each: 64 M cells = 16 MB, L2-resident next to the FP32 table), at most 2^7, and at
@@ -2122,7 +2139,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     // hot structures first: the L2-persisting window covers [0, hot_bytes) only, so the f64 records that
     // just the exact kernel reads do not compete for the cache with the tables every point touches
     const size_t raster_words = (size_t)idx->grid.fgy * (size_t)idx->grid.wpr;
-    const size_t o_raster = carve(sizeof(uint32_t) * (raster_words + 1));
+    const size_t o_raster = carve(sizeof(uint2) * (raster_words + 1));
     const size_t o_cand = carve(sizeof(int2) * n_cells);
     const size_t o_cells = carve(sizeof(CellRec) * n_cells);
     const size_t o_fast = carve(sizeof(float4) * (idx->n_fast + 8));
@@ -2145,7 +2162,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
     TRYF(ctx->alloc(off, &q));
     idx->slab = (uint8_t *)q;
     idx->slab_bytes = off;
-    idx->raster = (uint32_t *)(idx->slab + o_raster);
+    idx->raster = (uint2 *)(idx->slab + o_raster);
     idx->cand01 = (int2 *)(idx->slab + o_cand);
     idx->cells = (CellRec *)(idx->slab + o_cells);
     idx->parts = (PartRec *)(idx->slab + o_parts);

@@ -1,8 +1,8 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-T=r2f
-timeout 900 python -m pytest tests/test_gpu_pip.py tests/test_gpu_hull.py -q > gpurun_out/${T}_pytest_a.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_a.log
+T=r2g
+timeout 900 python -m pytest tests/test_gpu_pip.py tests/test_gpu_join.py tests/test_gpu_formats.py -q > gpurun_out/${T}_pytest_a.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_a.log
 tail -4 gpurun_out/${T}_pytest_a.log
 rm -f gpurun_out/${T}_exp.jsonl
 for cfg in "GPL_PIP_RASTER_LOG2=6"; do
@@ -13,7 +13,8 @@ import sys,json
 for l in sys.stdin:
     d=json.loads(l); print(d['tag'],'| build',round(d['build_ms_min'],3),'| query',round(d['query_ms_min'],3),'| chk',d['checksum'],'| phases us',d['fill_phases_us'])
 "
-for cfg in "GPL_HULL_MINB=5" "GPL_HULL_MINB=4"; do
+for cfg in "GPL_PIP_SLOTS_X100=600"; do env $cfg timeout 300 python tools/exp_pip2.py --reps 3 --tag "$cfg" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d[\"tag\"],\"| build\",round(d[\"build_ms_min\"],3),\"| query\",round(d[\"query_ms_min\"],3))"; done
+for cfg in "GPL_HULL_MINB=5"; do
   echo "== $cfg"; env $cfg timeout 600 python bench.py --workload c5 --points 3000000 --steps 3 --warmup 3 --no-e2e --no-cpu 2> gpurun_out/${T}_c5_$cfg.err | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print('c5 3M polys: ms/step',round(d['ms_per_step'],2))"
