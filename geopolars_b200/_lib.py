@@ -98,6 +98,8 @@ SIGNATURES = {
     "gpl_ctx_destroy": (None, [_P]),
     "gpl_ctx_trim": (_INT, [_P]),
     "gpl_ctx_launch_count": (_I64, [_P]),
+    "gpl_ctx_kernel_timing": (_INT, [_P, _INT]),
+    "gpl_ctx_kernel_timing_read": (_INT, [_P, C.POINTER(_D), C.POINTER(_I64)]),
     "gpl_host_alloc": (_INT, [C.c_size_t, C.POINTER(_P)]),
     "gpl_host_free": (None, [_P]),
     "gpl_array_from_buffers": (_INT, [_P, C.POINTER(Buffers), C.POINTER(_P)]),

@@ -205,6 +205,7 @@ extern "C" void gpl_ctx_destroy(gpl_ctx *ctx) {
         (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_prev_limit);
         (void)cudaGetLastError();
     }
+    for (cudaEvent_t ev : ctx->kt_events) cudaEventDestroy(ev);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -218,6 +219,46 @@ extern "C" int gpl_ctx_trim(gpl_ctx *ctx) {
     return GPL_OK;
 }
 extern "C" int64_t gpl_ctx_launch_count(const gpl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- kernel timing (measurement aid): event pairs around the streaming join kernel's launches ------------------
+bool gpl_ctx::kernel_timing_pair(cudaEvent_t *a, cudaEvent_t *b) {
+    constexpr size_t kMaxPairs = 4096;
+    if (kt_used + 2 > kt_events.size()) {
+        if (kt_events.size() >= 2 * kMaxPairs) return false;  // not read for a long time: stop recording
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (e0) cudaEventDestroy(e0);
+            return false;
+        }
+        kt_events.push_back(e0);
+        kt_events.push_back(e1);
+    }
+    *a = kt_events[kt_used], *b = kt_events[kt_used + 1];
+    kt_used += 2;
+    return true;
+}
+extern "C" int gpl_ctx_kernel_timing(gpl_ctx *ctx, int enable) {
+    GPL_REQUIRE(ctx != nullptr, GPL_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->kt_on = enable != 0;
+    if (!ctx->kt_on) ctx->kt_used = 0;
+    return GPL_OK;
+}
+extern "C" int gpl_ctx_kernel_timing_read(gpl_ctx *ctx, double *ms_total, int64_t *launches) {
+    GPL_REQUIRE(ctx && ms_total && launches, GPL_ERR_INVALID_ARG, "gpl_ctx_kernel_timing_read: NULL argument");
+    GPL_CUDA(cudaSetDevice(ctx->device));
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < ctx->kt_used; i += 2) {
+        GPL_CUDA(cudaEventSynchronize(ctx->kt_events[i + 1]));
+        float ms = 0.0f;
+        GPL_CUDA(cudaEventElapsedTime(&ms, ctx->kt_events[i], ctx->kt_events[i + 1]));
+        sum += (double)ms;
+    }
+    *ms_total = sum;
+    *launches = (int64_t)(ctx->kt_used / 2);
+    ctx->kt_used = 0;
+    return GPL_OK;
+}
 
 extern "C" int gpl_host_alloc(size_t bytes, void **out) {
     GPL_REQUIRE(out != nullptr, GPL_ERR_INVALID_ARG, "out is NULL");

@@ -66,6 +66,11 @@ struct gpl_ctx {
     const void *l2_pinned = nullptr;               // slab currently covered by the access-policy window
     size_t l2_prev_limit = 0, l2_cur_limit = 0;    // cudaLimitPersistingL2CacheSize before the first pin / now
     bool l2_limit_saved = false;
+    // gpl_ctx_kernel_timing: event pairs around the launches of the streaming join kernel (a measurement aid)
+    bool kt_on = false;
+    std::vector<cudaEvent_t> kt_events;  // pairs
+    size_t kt_used = 0;                  // events handed out since the last read
+    bool kernel_timing_pair(cudaEvent_t *a, cudaEvent_t *b);
 
     int alloc(size_t bytes, void **out);
     void release(void *p);

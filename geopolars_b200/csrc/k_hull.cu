@@ -33,6 +33,7 @@ struct HullFrame {  // pending "emit far, then hull_set(a, far, slice)" after th
 };
 
 __device__ __forceinline__ bool lex_less(double2 a, double2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+static __device__ __noinline__ double orient2d_noinline(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y); }
 static __device__ __noinline__ bool is_ccw_exact(double2 a, double2 b, double2 c) { return orient2d(a.x, a.y, b.x, b.y, c.x, c.y) > 0.0; }
 // strict-CCW test.  The stage-A filter decides almost every call inline; only an uncertified determinant takes
 // the out-of-line adaptive predicate (keeps the hot loops small: 122 -> ~80 registers).
@@ -383,7 +384,7 @@ __device__ __forceinline__ unsigned long long hull_ord(double d) {  // order-pre
     const unsigned long long b = (unsigned long long)__double_as_longlong(d);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
-template <bool WRITE, int MINB>
+template <bool WRITE, int MINB, bool FUSED>
 __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
                                                                const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
                                                                const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
@@ -422,16 +423,33 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                     if (mi < 0 || lex_less(q, mn)) mn = q, mi = i;
                     if (xi < 0 || lex_less(mx, q)) mx = q, xi = i;
                 }
+                // warp arg-min / arg-max of (x, then y, then lowest index) through REDUX on order-preserving keys: the 5-step
+                // butterfly over (x, y, index) cost ~250 instructions per polygon.  x + 0.0 maps -0.0 to +0.0 (equal as doubles).
+                {
+                    auto warp_pick = [&](bool want_max, double2 &v, int32_t &vi) {
+                        unsigned cand = __ballot_sync(0xffffffffu, vi >= 0);
+                        const double ord[2] = {v.x + 0.0, v.y + 0.0};
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ox = __shfl_xor_sync(0xffffffffu, mn.x, o), oy = __shfl_xor_sync(0xffffffffu, mn.y, o);
-                    const int32_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
-                    const double2 oq = make_double2(ox, oy);
-                    if (oi >= 0 && (mi < 0 || lex_less(oq, mn) || (!lex_less(mn, oq) && oi < mi))) mn = oq, mi = oi;
-                    const double px = __shfl_xor_sync(0xffffffffu, mx.x, o), py = __shfl_xor_sync(0xffffffffu, mx.y, o);
-                    const int32_t pi = __shfl_xor_sync(0xffffffffu, xi, o);
-                    const double2 pq = make_double2(px, py);
-                    if (pi >= 0 && (xi < 0 || lex_less(mx, pq) || (!lex_less(pq, mx) && pi < xi))) mx = pq, xi = pi;
+                        for (int d = 0; d < 2 && __popc(cand) > 1; ++d) {
+                            unsigned long long k = hull_ord(ord[d]);
+                            if (want_max) k = ~k;  // arg-max as arg-min of the complement
+                            const bool in = (cand >> lane) & 1u;
+                            const uint32_t h = __reduce_min_sync(0xffffffffu, in ? (uint32_t)(k >> 32) : 0xffffffffu);
+                            const bool c1 = in && (uint32_t)(k >> 32) == h;
+                            const uint32_t l = __reduce_min_sync(0xffffffffu, c1 ? (uint32_t)k : 0xffffffffu);
+                            cand = __ballot_sync(0xffffffffu, c1 && (uint32_t)k == l);
+                        }
+                        if (__popc(cand) > 1) {  // equal coordinates: the lowest index (any instance would do)
+                            const bool in = (cand >> lane) & 1u;
+                            const uint32_t i0 = __reduce_min_sync(0xffffffffu, in ? (uint32_t)vi : 0xffffffffu);
+                            cand = __ballot_sync(0xffffffffu, in && (uint32_t)vi == i0);
+                        }
+                        const int src = __ffs(cand) - 1;  // n >= 4: at least one lane holds a point
+                        v.x = __shfl_sync(0xffffffffu, v.x, src), v.y = __shfl_sync(0xffffffffu, v.y, src);
+                        vi = __shfl_sync(0xffffffffu, vi, src);
+                    };
+                    warp_pick(false, mn, mi);
+                    warp_pick(true, mx, xi);
                 }
                 flag = __any_sync(0xffffffffu, bad) || (mn.x == mx.x && mn.y == mx.y);
                 int32_t m = 2, ne = 0;  // chain length, live points
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                             const double det = dl - dr;
                             if (fabs(det) > kCcwA * (fabs(dl) + fabs(dr))) side = det > 0.0 ? 1 : 2;
                             else {
-                                const double ex = orient2d(mx.x, mx.y, mn.x, mn.y, q.x, q.y);
+                                const double ex = orient2d_noinline(mx, mn, q);
                                 side = ex > 0.0 ? 1 : (ex < 0.0 ? 2 : 0);
                             }
                         }
@@ -460,32 +478,67 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                     __syncwarp();
                 }
                 // ---- one iteration per recursion depth
-                while (!flag && ne > 0) {
-                    for (int32_t j = lane; j < m; j += 32) HI[j] = 0u, LO[j] = 0u;
+                // zero the per-call maxima of the first `cnt` calls
+                auto zero_calls = [&](int32_t cnt) {
+                    for (int32_t j = lane; j < cnt; j += 32) HI[j] = 0u, LO[j] = 0u;
                     __syncwarp();
-                    // A: per call, the maximum of orth(a,b) . (p - a): high word first
-                    for (int32_t c = 0; c < ne; c += 32) {
-                        const int32_t e = c + lane;
-                        uint32_t hi = 0u, sg = 0xffffffffu;
-                        if (e < ne) {
-                            const uint32_t w = E[e];
-                            sg = w >> 16;
-                            const double2 p = P0[w & 0xffffu], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]];
+                };
+                // A: per call, the maximum of orth(a,b) . (p - a): high word first.  Two rows of 32 points per round, all
+                // loads of both rows issued before the first use (the chain E -> CH -> P0 is three dependent shared loads).
+                auto pass_a = [&]() {
+                    for (int32_t c = 0; c < ne; c += 64) {
+                        uint32_t sgv[2], hiv[2];
+                        unsigned long long kv[2];
+                        bool inr[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int32_t e = c + 32 * u + lane;
+                            inr[u] = e < ne;
+                            const uint32_t w = E[inr[u] ? e : 0];
+                            sgv[u] = w >> 16;
+                            const double2 p = P0[w & 0xffffu], a = P0[CH[sgv[u]]], b = P0[CH[sgv[u] ? sgv[u] - 1 : m - 1]];
                             const double ox = a.y - b.y, oy = b.x - a.x, dx = p.x - a.x, dy = p.y - a.y;
-                            const unsigned long long k = hull_ord(ox * dx + oy * dy);
-                            KV[e] = k;
-                            hi = (uint32_t)(k >> 32);
+                            kv[u] = hull_ord(ox * dx + oy * dy);
+                            hiv[u] = inr[u] ? (uint32_t)(kv[u] >> 32) : 0u;
                         }
-                        const uint32_t sg0 = __shfl_sync(0xffffffffu, sg, 0);
-                        if (__all_sync(0xffffffffu, sg == sg0)) {  // a whole row of one call: one atomic instead of 32 colliding ones
-                            const uint32_t r = __reduce_max_sync(0xffffffffu, hi);
-                            if (lane == 0) atomicMax(&HI[sg0], r);
-                        } else if (e < ne) {
-                            atomicMax(&HI[sg], hi);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            if (inr[u]) KV[c + 32 * u + lane] = kv[u];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (c + 32 * u >= ne) break;  // warp-uniform
+                            const uint32_t sg0 = __shfl_sync(0xffffffffu, sgv[u], 0);
+                            if (__all_sync(0xffffffffu, !inr[u] || sgv[u] == sg0)) {  // a whole row of one call: one atomic instead of 32 colliding ones
+                                const uint32_t r = __reduce_max_sync(0xffffffffu, hiv[u]);
+                                if (lane == 0) atomicMax(&HI[sg0], r);
+                            } else if (inr[u]) {
+                                atomicMax(&HI[sgv[u]], hiv[u]);
+                            }
                         }
                     }
                     __syncwarp();
-                    // B: low word among the points that hold the high word
+                };
+                // B: the far point of every live call = the point holding the call's maximal key.  Returns true when two points
+                // with different coordinates tie somewhere (geo's slice order would decide — not reproduced here).
+                auto pass_b = [&]() -> bool {
+                    // the points that hold their call's high word; one per call (nearly always): it is the far point
+                    bool multi = false;
+                    for (int32_t c = 0; c < ne; c += 32) {
+                        const int32_t e = c + lane;
+                        if (e < ne) {
+                            const uint32_t w = E[e], sg = w >> 16;
+                            if ((uint32_t)(KV[e] >> 32) == HI[sg]) {
+                                multi = multi || atomicAdd(&LO[sg], 1u) > 0u;
+                                FAR[sg] = (int32_t)(w & 0xffffu);
+                            }
+                        }
+                    }
+                    const bool any_multi = __any_sync(0xffffffffu, multi);
+                    __syncwarp();
+                    if (!any_multi) return false;
+                    // several points share a high word somewhere: low word among them, then the holder(s) of the full key
+                    for (int32_t j = lane; j < m; j += 32) LO[j] = 0u;
+                    __syncwarp();
                     for (int32_t c = 0; c < ne; c += 32) {
                         const int32_t e = c + lane;
                         if (e < ne) {
@@ -495,7 +548,6 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                         }
                     }
                     __syncwarp();
-                    // C: any point holding the maximum becomes the call's far point
                     for (int32_t c = 0; c < ne; c += 32) {
                         const int32_t e = c + lane;
                         if (e < ne) {
@@ -505,7 +557,6 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                         }
                     }
                     __syncwarp();
-                    // D: a different point with the same value: geo's slice order would decide — not reproduced here
                     bool tie = false;
                     for (int32_t c = 0; c < ne; c += 32) {
                         const int32_t e = c + lane;
@@ -518,7 +569,18 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                             }
                         }
                     }
-                    if (__any_sync(0xffffffffu, tie)) {
+                    return __any_sync(0xffffffffu, tie);
+                };
+                if (FUSED && !flag && ne > 0) {
+                    zero_calls(m);
+                    pass_a();
+                }
+                while (!flag && ne > 0) {
+                    if (!FUSED) {
+                        zero_calls(m);
+                        pass_a();
+                    }
+                    if (pass_b()) {
                         flag = true;
                         break;
                     }
@@ -541,27 +603,54 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                         break;
                     }
                     __syncwarp();
-                    // E: every point moves to one of its call's two children, or drops out
+                    if (FUSED) zero_calls(m + added);  // the next level's maxima are formed while the points move
+                    // E: every point moves to one of its call's two children, or drops out (two rows per round, as in A).
+                    // FUSED: its key in the child call (a', b') = (far, b) or (a, far) is formed here, from the coordinates already
+                    // in registers — the same expression pass A evaluates.
                     int32_t ne2 = 0;
                     bool both = false;
-                    for (int32_t c = 0; c < ne; c += 32) {
-                        const int32_t e = c + lane;
-                        uint32_t nw = 0u;
-                        bool keep = false;
-                        if (e < ne) {
-                            const uint32_t w = E[e], sg = w >> 16, pi = w & 0xffffu;
+                    for (int32_t c = 0; c < ne; c += 64) {
+                        uint32_t nw[2], hi2[2];
+                        unsigned long long k2[2];
+                        bool keep[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int32_t e = c + 32 * u + lane;
+                            const bool in = e < ne;
+                            const uint32_t w = E[in ? e : 0], sg = w >> 16, pi = w & 0xffffu;
                             const int32_t nj = NI[sg];
-                            const double2 p = P0[pi], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]], f = P0[CHn[nj - 1]];
-                            if (!(p.x == f.x && p.y == f.y)) {
+                            const double2 p = P0[pi], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]], f = P0[FAR[sg]];
+                            keep[u] = false, nw[u] = 0u, k2[u] = 0ULL;
+                            if (in && !(p.x == f.x && p.y == f.y)) {
                                 const bool t1 = is_ccw(f, b, p), t2 = is_ccw(a, f, p);
                                 both = both || (t1 && t2);
-                                keep = t1 || t2;
-                                nw = pi | ((uint32_t)(t1 ? nj - 1 : nj) << 16);
+                                keep[u] = t1 || t2;
+                                nw[u] = pi | ((uint32_t)(t1 ? nj - 1 : nj) << 16);
+                                if (FUSED) {
+                                    const double2 a2 = t1 ? f : a, b2 = t1 ? b : f;
+                                    const double ox = a2.y - b2.y, oy = b2.x - a2.x, dx = p.x - a2.x, dy = p.y - a2.y;
+                                    k2[u] = hull_ord(ox * dx + oy * dy);
+                                }
                             }
+                            hi2[u] = keep[u] ? (uint32_t)(k2[u] >> 32) : 0u;
                         }
-                        const unsigned mk = __ballot_sync(0xffffffffu, keep);
-                        if (keep) En[ne2 + __popc(mk & below)] = nw;
-                        ne2 += __popc(mk);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const unsigned mk = __ballot_sync(0xffffffffu, keep[u]);
+                            const int32_t pos = ne2 + __popc(mk & below);
+                            if (keep[u]) En[pos] = nw[u];
+                            if (FUSED && mk) {
+                                if (keep[u]) KV[pos] = k2[u];
+                                const uint32_t nc = nw[u] >> 16, c0 = __shfl_sync(0xffffffffu, nc, __ffs(mk) - 1);
+                                if (__all_sync(0xffffffffu, !keep[u] || nc == c0)) {
+                                    const uint32_t r = __reduce_max_sync(0xffffffffu, hi2[u]);
+                                    if (lane == 0) atomicMax(&HI[c0], r);
+                                } else if (keep[u]) {
+                                    atomicMax(&HI[nc], hi2[u]);
+                                }
+                            }
+                            ne2 += __popc(mk);
+                        }
                     }
                     if (__any_sync(0xffffffffu, both)) {
                         flag = true;
@@ -666,20 +755,31 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         const char *e = getenv("GPL_HULL_MINB");
         return e ? atoi(e) : 5;
     }();
+    // GPL_HULL_FUSED=0: the next level's keys in a pass of their own (A/B switch for the fused move + key pass)
+    static const bool fast_fused = [] {
+        const char *e = getenv("GPL_HULL_FUSED");
+        return !e || atoi(e) != 0;
+    }();
+    using FastKernel = void (*)(int, int64_t, const double2 *, const int64_t *, const int64_t *, const int64_t *, const uint8_t *, int32_t,
+                                int64_t *, const int64_t *, double2 *, uint8_t *);
+    // [write][fused]
+    FastKernel fast_k[2][2];
+    if (fast_minb >= 5) {
+        fast_k[0][0] = k_hull_fast<false, 5, false>, fast_k[0][1] = k_hull_fast<false, 5, true>;
+        fast_k[1][0] = k_hull_fast<true, 5, false>, fast_k[1][1] = k_hull_fast<true, 5, true>;
+    } else {
+        fast_k[0][0] = k_hull_fast<false, 4, false>, fast_k[0][1] = k_hull_fast<false, 4, true>;
+        fast_k[1][0] = k_hull_fast<true, 4, false>, fast_k[1][1] = k_hull_fast<true, 4, true>;
+    }
     const int32_t fast_cap = (int32_t)((std::min<unsigned long long>(std::max<unsigned long long>(h_max, 4), 1024) + 1) & ~1ULL);
     const size_t fast_smem = HullFastLayout::bytes(fast_cap) * kHullWarps;
     int fast_grid = 1;
     Scratch<uint8_t> redo;
     if (fast_enabled && n > 0) {
         GPL_TRY(redo.get(ctx, (size_t)n));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        for (int w = 0; w < 2; ++w) GPL_CUDA(cudaFuncSetAttribute(fast_k[w][fast_fused], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
         int occ = 1;
-        const cudaError_t oe = fast_minb >= 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true, 5>, kHullWarps * 32, fast_smem)
-                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true, 4>, kHullWarps * 32, fast_smem);
-        if (oe != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_k[1][fast_fused], kHullWarps * 32, fast_smem) != cudaSuccess || occ < 1) occ = 1;
         (void)cudaGetLastError();
         fast_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kHullWarps), (int64_t)kSMs * occ));
     }
@@ -688,15 +788,8 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         if (n == 0) return GPL_OK;
         const uint8_t *only = nullptr;
         if (fast_enabled) {
-#define GPL_HULL_FAST_LAUNCH(W, B) k_hull_fast<W, B><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity, fast_cap, cnt, off, dst, redo.p)
-            if (fast_minb >= 5) {
-                if (write) GPL_HULL_FAST_LAUNCH(true, 5);
-                else GPL_HULL_FAST_LAUNCH(false, 5);
-            } else {
-                if (write) GPL_HULL_FAST_LAUNCH(true, 4);
-                else GPL_HULL_FAST_LAUNCH(false, 4);
-            }
-#undef GPL_HULL_FAST_LAUNCH
+            fast_k[write ? 1 : 0][fast_fused]<<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
+                                                                                                   in->validity, fast_cap, cnt, off, dst, redo.p);
             ctx->launches++;
             only = redo.p;
         }

@@ -889,12 +889,16 @@ __device__ __forceinline__ uint32_t raster_rank_code(const BuildArgs &a, const G
     if (s + 1 < e && a.items[s + 1] == part) return 2u;
     return 3u;
 }
-// OR the inside code of `part` over cells [lo, hi] of fine row fy (the code depends on the coarse column)
+// OR the inside code of `part` over cells [lo, hi] of fine row fy (the code depends on the coarse column).
+// `codes` (or nullptr): the part's codes in the coarse cells of its bbox, row-major from (cx0, cy0), ncx per row — the two
+// dependent global loads of raster_rank_code per span were the latency of the whole phase.
 __device__ __forceinline__ void raster_fill_span(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start,
-                                                 int32_t fy, int32_t lo, int32_t hi, int32_t part) {
+                                                 int32_t fy, int32_t lo, int32_t hi, int32_t part, const uint8_t *codes, int32_t cx0,
+                                                 int32_t cy0, int32_t ncx) {
     for (int32_t cc = lo >> g.rs; cc <= (hi >> g.rs); ++cc) {
         const int32_t x0 = max(lo, cc << g.rs), x1 = min(hi, ((cc + 1) << g.rs) - 1);
-        raster_or_span(a.raster, g.wpr, fy, x0, x1, raster_rank_code(a, g, cell_start, cc, fy >> g.rs, part));
+        const uint32_t code = codes ? (uint32_t)codes[((fy >> g.rs) - cy0) * ncx + (cc - cx0)] : raster_rank_code(a, g, cell_start, cc, fy >> g.rs, part);
+        raster_or_span(a.raster, g.wpr, fy, x0, x1, code);
     }
 }
 
@@ -914,11 +918,13 @@ __device__ __forceinline__ void raster_fill_span(const BuildArgs &a, const GridP
 // exactly.  Everything the lists cannot hold (more than kRowCross crossings in a row, a row whose centre does not map
 // back to it) is coded 3 over the part's whole column range, which is always safe.
 constexpr int kRowCross = 24;  // a horizontal line through a config-2 star crosses 12-17 edges
+constexpr int kRasterCodeCells = 64;  // coarse cells of a part's bbox whose codes are staged (a config-2 part covers 4-9)
 constexpr int kRowStride = kRowCross + 1;  // odd stride: the 32 lists of a chunk do not collide on banks
 struct RasterSmem {
     double ry[kBuildThreads / 32][32];  // centre-line ordinate of every row of the chunk (one division per row, not per edge)
     int32_t cnt[kBuildThreads / 32][32];
     uint32_t list[kBuildThreads / 32][32 * kRowStride];  // cell (20 bits) | down (bit 20) | ring (bits 21..31, saturated)
+    uint8_t code[kBuildThreads / 32][kRasterCodeCells];   // the part's inside code in every coarse cell of its bbox
 };
 __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t *__restrict__ cell_start, RasterSmem &sm) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -928,7 +934,13 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
     int32_t *cnt = sm.cnt[wid];
     uint32_t *list = sm.list[wid];
     double *row_y = sm.ry[wid];
-    for (int64_t p = warp; p < a.P; p += nwarps) {
+    // work item = (part, k): the chunks ra = fy0 + 32 (k + K j) of the part.  A part's bbox is about one coarse cell high,
+    // i.e. K = 2^rs / 32 chunks; they are independent (every raster write is an atomicOr), so config 4's 1 000 parts keep
+    // 4 000 warps busy instead of 1 000.
+    const int32_t K = max(1, min(8, (1 << g.rs) >> 5));
+    for (int64_t it = warp; it < a.P * K; it += nwarps) {
+        const int64_t p = it / K;
+        const int32_t kk = (int32_t)(it - p * K);
         const PartHeader h = a.hdr[p];
         if (!(h.flags & 2)) continue;
         int64_t r0, r1;
@@ -936,7 +948,16 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
         const int32_t fx0 = fine_index(h.xmin, g.x0, g.inv_fw, g.fgx), fx1 = fine_index(h.xmax, g.x0, g.inv_fw, g.fgx);
         const int32_t fy0 = fine_index(h.ymin, g.y0, g.inv_fh, g.fgy), fy1 = fine_index(h.ymax, g.y0, g.inv_fh, g.fgy);
         bool irregular = false;
-        for (int32_t ra = fy0; ra <= fy1; ra += 32) {
+        // the part's inside code per coarse cell of its bbox, once per part
+        const int32_t cx0 = fx0 >> g.rs, cy0 = fy0 >> g.rs, ncx = (fx1 >> g.rs) - cx0 + 1, ncy = (fy1 >> g.rs) - cy0 + 1;
+        const bool staged = (int64_t)ncx * ncy <= kRasterCodeCells;
+        const uint8_t *codes = staged ? sm.code[wid] : nullptr;
+        __syncwarp();  // the previous part's rows are done with the table
+        if (staged)
+            for (int32_t k = lane; k < ncx * ncy; k += 32)
+                sm.code[wid][k] = (uint8_t)raster_rank_code(a, g, cell_start, cx0 + k % ncx, cy0 + k / ncx, (int32_t)p);
+        __syncwarp();
+        for (int32_t ra = fy0 + 32 * kk; ra <= fy1; ra += 32 * K) {
             const int32_t rb = min(ra + 31, fy1);
             cnt[lane] = 0;
             row_y[lane] = g.y0 + ((double)(ra + lane) + 0.5) / g.inv_fh;
@@ -998,6 +1019,17 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
                         }
                         L[j + 1] = v;
                     }
+                    if (r1 - r0 == 1) {
+                        // a part without holes: the winding number of interval k is the sum of the directions of entries k..n-1 —
+                        // a running sum from the right (the general loop below recomputes it per interval: O(n^2) per row, and a
+                        // config-2 star has 12-17 crossings per row)
+                        int wn = 0;
+                        for (int k = n - 1; k >= 1; --k) {
+                            wn += (L[k] & (1u << 20)) ? -1 : 1;
+                            const int32_t lo = (int32_t)(L[k - 1] & 0xfffffu) + 1, hi = (int32_t)(L[k] & 0xfffffu) - 1;
+                            if (lo <= hi && wn != 0) raster_fill_span(a, g, cell_start, fy, lo, hi, (int32_t)p, codes, cx0, cy0, ncx);
+                        }
+                    } else
                     for (int k = 1; k < n; ++k) {  // cells strictly between crossing k-1 and crossing k
                         const int32_t lo = (int32_t)(L[k - 1] & 0xfffffu) + 1, hi = (int32_t)(L[k] & 0xfffffu) - 1;
                         if (lo > hi) continue;
@@ -1023,7 +1055,7 @@ __device__ void ph_raster(const BuildArgs &a, const GridParams &g, const int32_t
                         bool saturated = false;
                         for (int j = k; j < n; ++j) saturated = saturated || (L[j] >> 21) == 2047u;
                         if (saturated) raster_or_span(a.raster, g.wpr, fy, lo, hi, 3u);
-                        else if (wn_ext != 0 && !in_hole) raster_fill_span(a, g, cell_start, fy, lo, hi, (int32_t)p);
+                        else if (wn_ext != 0 && !in_hole) raster_fill_span(a, g, cell_start, fy, lo, hi, (int32_t)p, codes, cx0, cy0, ncx);
                     }
                 }
             }
@@ -1532,6 +1564,21 @@ struct __align__(16) StreamSmem {
 __device__ __forceinline__ void ld256s(const double2 *p, double2 &a, double2 &b) {  // read-once stream: evict first
     asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
+// cache-hint variants (GPL_PIP_LD_HINTS, A/B switch): the point stream without an L1 line (L2: evict first), the raster gather
+// (20 MB of random 8-byte words: no reuse an L1 could catch) without one — leaves the L1 to the cell / part / edge records.
+__device__ __forceinline__ void ld256s_na(const double2 *p, double2 &a, double2 &b, unsigned long long pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y)
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld256s_na0(const double2 *p, double2 &a, double2 &b) {
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ uint2 ldg_na(const uint2 *p) {
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 // HIST: per-polygon hit counts (config 4's all-reduce input) in the same pass: 32-bit bins privatised per CTA in shared
 // memory behind the queues, flushed with one 64-bit global atomic per non-zero bin when the CTA retires.
 // CSM: the rows of candidate #0 of every coarse cell (raster code 1: 36 % of config 2's points) staged in shared memory —
@@ -1542,8 +1589,12 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
                                                                                   int32_t *__restrict__ first_id, int32_t *__restrict__ count,
                                                                                   unsigned long long *__restrict__ n_deferred,
                                                                                   uint32_t *__restrict__ deferred_list, uint32_t list_cap,
-                                                                                  int vec_ok, unsigned long long *__restrict__ hist, int32_t n_bins) {
+                                                                                  int vec_ok, unsigned long long *__restrict__ hist, int32_t n_bins,
+                                                                                  int hints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long pol_ef = 0ULL;
+    if (hints & 2) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ef));
+    const bool raster_na = (hints & 1) != 0, pts_na = (hints & 2) != 0;
     StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
     unsigned int *bins = reinterpret_cast<unsigned int *>(smem_raw + sizeof(StreamSmem));
     int32_t *cand0 = reinterpret_cast<int32_t *>(smem_raw + sizeof(StreamSmem));  // HIST and CSM are never combined
@@ -1592,8 +1643,16 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
     auto load_tile = [&](int64_t t, double2 (&dst)[4]) {
         const int64_t base = t * kTilePts;
         if (vec_ok && base + kTilePts <= n_pts) {
-            ld256s(pts + base + 2 * lane, dst[0], dst[1]);
-            ld256s(pts + base + 64 + 2 * lane, dst[2], dst[3]);
+            if (pts_na) {
+                ld256s_na(pts + base + 2 * lane, dst[0], dst[1], pol_ef);
+                ld256s_na(pts + base + 64 + 2 * lane, dst[2], dst[3], pol_ef);
+            } else if (hints & 4) {
+                ld256s_na0(pts + base + 2 * lane, dst[0], dst[1]);
+                ld256s_na0(pts + base + 64 + 2 * lane, dst[2], dst[3]);
+            } else {
+                ld256s(pts + base + 2 * lane, dst[0], dst[1]);
+                ld256s(pts + base + 64 + 2 * lane, dst[2], dst[3]);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1620,7 +1679,8 @@ __global__ void __launch_bounds__(kQueryThreads, GPL_PIP_STREAM_MINB) k_pip_stre
             if (i >= n_pts) ok[k] = false;
             if (ok[k] && pts_validity) ok[k] = bit_get(pts_validity, i);
             fx[k] = fine_index(p[k].x, g.x0, g.inv_fw, g.fgx), fy[k] = fine_index(p[k].y, g.y0, g.inv_fh, g.fgy);
-            word[k] = ok[k] ? __ldg(ix.raster + (int64_t)fy[k] * g.wpr + (fx[k] >> 4)) : make_uint2(0u, 0u);
+            const uint2 *wp = ix.raster + (int64_t)fy[k] * g.wpr + (fx[k] >> 4);
+            word[k] = ok[k] ? (raster_na ? ldg_na(wp) : __ldg(wp)) : make_uint2(0u, 0u);
         }
         // stage 2: codes -> ids
         int32_t id[4];
@@ -1814,16 +1874,19 @@ template <bool LEAN, bool HIST>
 static void launch_stream(const IndexView &v, const double2 *pts, const uint8_t *val, int64_t m, int32_t *first, int32_t *cnt,
                           const gpl_pip_index *idx, int vec_ok, unsigned long long *hist, int32_t n_bins, cudaStream_t stream) {
     static const bool csm_enabled = env_int("GPL_PIP_CAND_SMEM", 0) != 0;  // measured slower on config 2 (0.98 vs 0.90 ms): opt-in
+    // bit 0: raster gather without an L1 line; bit 2: the point stream too; bit 1: the point stream too, plus an L2 evict-first
+    // policy.  Query ms, config 2 / config 4:  0: 0.846 / 0.856   1: 0.821 / 0.832   5: 0.819 / 0.827   3: 0.812 / 0.955
+    static const int hints = env_int("GPL_PIP_LD_HINTS", 5);
     const int64_t n_cells = (int64_t)v.grid.gx * v.grid.gy;
     if (!HIST && csm_enabled && n_cells <= kCandSmemMaxCells) {
         const size_t smem = sizeof(StreamSmem) + sizeof(int32_t) * (size_t)n_cells;
         k_pip_stream<LEAN, false, true><<<stream_grid<LEAN, false, true>(m, smem), kQueryThreads, smem, stream>>>(
-            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, nullptr, 0);
+            v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, nullptr, 0, hints);
         return;
     }
     const size_t smem = sizeof(StreamSmem) + (HIST ? sizeof(unsigned int) * (size_t)n_bins : 0);
     k_pip_stream<LEAN, HIST, false><<<stream_grid<LEAN, HIST, false>(m, smem), kQueryThreads, smem, stream>>>(
-        v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins);
+        v, pts, val, m, first, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap, vec_ok, hist, n_bins, hints);
 }
 // hist (optional, device, n_geoms u64): += number of points whose first containing row is that polygon
 int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, const uint8_t *validity_dev, int64_t n,
@@ -1862,6 +1925,8 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
                                                                                      nullptr, lo, idx->n_deferred, idx->deferred_list,
                                                                                      idx->deferred_cap);
         } else {
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (ctx->kt_on && ctx->kernel_timing_pair(&t0, &t1)) GPL_CUDA(cudaEventRecord(t0, stream));
             // 256-bit point loads and 64-bit id stores need 32- / 8-byte aligned columns (cudaMalloc'd ones are)
             const int vec_ok = ((reinterpret_cast<uintptr_t>(pts + lo) & 31) == 0 && (reinterpret_cast<uintptr_t>(first_dev + lo) & 7) == 0 &&
                                 (cnt == nullptr || (reinterpret_cast<uintptr_t>(cnt) & 7) == 0))
@@ -1875,9 +1940,10 @@ int pip_query(gpl_ctx *ctx, const gpl_pip_index *idx, const double *pts_dev, con
                 if (fuse_hist) launch_stream<false, true>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, hist, nb, stream);
                 else launch_stream<false, false>(v, pts + lo, val, m, first_dev + lo, cnt, idx, vec_ok, nullptr, 0, stream);
             }
+            if (t1) GPL_CUDA(cudaEventRecord(t1, stream));
         }
         const bool fused_here = fuse_hist && !legacy;
-        k_pip_deferred<<<kSMs * 2, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap,
+        k_pip_deferred<<<kSMs * 8, 256, 0, stream>>>(v, pts + lo, m, first_dev + lo, cnt, idx->n_deferred, idx->deferred_list, idx->deferred_cap,
                                                      idx->n_deferred + 1, fused_here ? hist : nullptr);
         ctx->launches += 2;
         if (hist && !fused_here) {  // many polygons (or the legacy kernel): count from the id column

@@ -47,6 +47,16 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.gpl_ctx_launch_count(self._h))
 
+    def kernel_timing(self, enable: bool) -> None:
+        """bracket every launch of the streaming join kernel with CUDA events (measurement aid, see the header)"""
+        check(self.lib.gpl_ctx_kernel_timing(self._h, 1 if enable else 0))
+
+    def kernel_timing_read(self):
+        """(summed ms, launches) of the bracketed launches since the previous read; waits for them"""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(self.lib.gpl_ctx_kernel_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self.lib.gpl_ctx_destroy(self._h)

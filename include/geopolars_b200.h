@@ -120,6 +120,12 @@ const char *gpl_last_error(void);
 int gpl_ctx_create(int device, void *stream, gpl_ctx **out);
 int gpl_ctx_set_stream(gpl_ctx *ctx, void *stream);
 int gpl_ctx_synchronize(gpl_ctx *ctx);
+/* Measurement aid (bench.py's roofline line): while enabled, every launch of the streaming points-in-polygons kernel
+ * (k_pip_stream, the kernel behind gpl_contains_join* — reference path spatial_index.rs:139-157 + geo `Contains`) on this
+ * context is bracketed by two CUDA events on the context's stream.  _read waits for the recorded pairs and returns their
+ * summed duration (ms) and count since the previous read. */
+int gpl_ctx_kernel_timing(gpl_ctx *ctx, int enable);
+int gpl_ctx_kernel_timing_read(gpl_ctx *ctx, double *ms_total, int64_t *launches);
 void gpl_ctx_destroy(gpl_ctx *ctx);
 /* give the cached (free) device blocks of the context's allocator back to the driver */
 int gpl_ctx_trim(gpl_ctx *ctx);

@@ -310,3 +310,23 @@ def test_join_counts_fused_histogram(ctx, og, conv):
         assert np.array_equal(counts.astype(np.int64), np.bincount(want[want >= 0], minlength=m))
         f2, c2 = idx.query_counts(pts)  # counts accumulate per call from a zeroed column: same result again
         assert np.array_equal(f2, want) and np.array_equal(c2, counts)
+
+
+def test_kernel_timing_brackets_every_stream_launch(ctx):
+    """gpl_ctx_kernel_timing (bench.py's roofline denominator): one event pair per k_pip_stream launch, read once"""
+    from geopolars_b200.engine import PipIndex
+
+    xy, ro, go = synth.star_polygons(100, 10)
+    idx = PipIndex(ctx.upload(GeoArrowArray.polygons(xy, ro, go)))
+    pts = synth.uniform_points(500_000, scale=100.0)
+    base = idx.query(pts)
+    assert ctx.kernel_timing_read() == (0.0, 0)  # off: nothing recorded
+    ctx.kernel_timing(True)
+    for _ in range(3):
+        assert np.array_equal(idx.query(pts), base)
+    ms, n = ctx.kernel_timing_read()
+    assert n == 3 and 0.0 < ms < 100.0
+    assert ctx.kernel_timing_read() == (0.0, 0)  # a read consumes the pairs
+    ctx.kernel_timing(False)
+    idx.query(pts)
+    assert ctx.kernel_timing_read() == (0.0, 0)
