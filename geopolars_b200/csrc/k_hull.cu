@@ -384,8 +384,8 @@ __device__ __forceinline__ unsigned long long hull_ord(double d) {  // order-pre
     const unsigned long long b = (unsigned long long)__double_as_longlong(d);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
-template <bool WRITE, int MINB, bool FUSED>
-__global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
+template <bool WRITE>
+__global__ void __launch_bounds__(kHullWarps * 32, 5) k_hull_fast(int type, int64_t n_geoms, const double2 *__restrict__ xy,
                                                                const int64_t *__restrict__ geom_off, const int64_t *__restrict__ part_off,
                                                                const int64_t *__restrict__ ring_off, const uint8_t *__restrict__ validity,
                                                                int32_t cap, int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
@@ -571,15 +571,9 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                     }
                     return __any_sync(0xffffffffu, tie);
                 };
-                if (FUSED && !flag && ne > 0) {
+                while (!flag && ne > 0) {
                     zero_calls(m);
                     pass_a();
-                }
-                while (!flag && ne > 0) {
-                    if (!FUSED) {
-                        zero_calls(m);
-                        pass_a();
-                    }
                     if (pass_b()) {
                         flag = true;
                         break;
@@ -603,15 +597,13 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                         break;
                     }
                     __syncwarp();
-                    if (FUSED) zero_calls(m + added);  // the next level's maxima are formed while the points move
                     // E: every point moves to one of its call's two children, or drops out (two rows per round, as in A).
-                    // FUSED: its key in the child call (a', b') = (far, b) or (a, far) is formed here, from the coordinates already
-                    // in registers — the same expression pass A evaluates.
+                    // (Forming the child call's key here, from the coordinates already in registers, saves pass A's loads but
+                    // measured slower: 33.0 vs 28.2 ms per 3 M polygons — more live registers, more spills.)
                     int32_t ne2 = 0;
                     bool both = false;
                     for (int32_t c = 0; c < ne; c += 64) {
-                        uint32_t nw[2], hi2[2];
-                        unsigned long long k2[2];
+                        uint32_t nw[2];
                         bool keep[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
@@ -620,35 +612,18 @@ __global__ void __launch_bounds__(kHullWarps * 32, MINB) k_hull_fast(int type, i
                             const uint32_t w = E[in ? e : 0], sg = w >> 16, pi = w & 0xffffu;
                             const int32_t nj = NI[sg];
                             const double2 p = P0[pi], a = P0[CH[sg]], b = P0[CH[sg ? sg - 1 : m - 1]], f = P0[FAR[sg]];
-                            keep[u] = false, nw[u] = 0u, k2[u] = 0ULL;
+                            keep[u] = false, nw[u] = 0u;
                             if (in && !(p.x == f.x && p.y == f.y)) {
                                 const bool t1 = is_ccw(f, b, p), t2 = is_ccw(a, f, p);
                                 both = both || (t1 && t2);
                                 keep[u] = t1 || t2;
                                 nw[u] = pi | ((uint32_t)(t1 ? nj - 1 : nj) << 16);
-                                if (FUSED) {
-                                    const double2 a2 = t1 ? f : a, b2 = t1 ? b : f;
-                                    const double ox = a2.y - b2.y, oy = b2.x - a2.x, dx = p.x - a2.x, dy = p.y - a2.y;
-                                    k2[u] = hull_ord(ox * dx + oy * dy);
-                                }
                             }
-                            hi2[u] = keep[u] ? (uint32_t)(k2[u] >> 32) : 0u;
                         }
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const unsigned mk = __ballot_sync(0xffffffffu, keep[u]);
-                            const int32_t pos = ne2 + __popc(mk & below);
-                            if (keep[u]) En[pos] = nw[u];
-                            if (FUSED && mk) {
-                                if (keep[u]) KV[pos] = k2[u];
-                                const uint32_t nc = nw[u] >> 16, c0 = __shfl_sync(0xffffffffu, nc, __ffs(mk) - 1);
-                                if (__all_sync(0xffffffffu, !keep[u] || nc == c0)) {
-                                    const uint32_t r = __reduce_max_sync(0xffffffffu, hi2[u]);
-                                    if (lane == 0) atomicMax(&HI[c0], r);
-                                } else if (keep[u]) {
-                                    atomicMax(&HI[nc], hi2[u]);
-                                }
-                            }
+                            if (keep[u]) En[ne2 + __popc(mk & below)] = nw[u];
                             ne2 += __popc(mk);
                         }
                     }
@@ -750,36 +725,16 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         const char *e = getenv("GPL_HULL_FAST");
         return !e || atoi(e) != 0;
     }();
-    // resident CTAs per SM the level-wise kernel is compiled for: 5 (96 registers, a few spills) or 4 (128 registers)
-    static const int fast_minb = [] {
-        const char *e = getenv("GPL_HULL_MINB");
-        return e ? atoi(e) : 5;
-    }();
-    // GPL_HULL_FUSED=0: the next level's keys in a pass of their own (A/B switch for the fused move + key pass)
-    static const bool fast_fused = [] {
-        const char *e = getenv("GPL_HULL_FUSED");
-        return !e || atoi(e) != 0;
-    }();
-    using FastKernel = void (*)(int, int64_t, const double2 *, const int64_t *, const int64_t *, const int64_t *, const uint8_t *, int32_t,
-                                int64_t *, const int64_t *, double2 *, uint8_t *);
-    // [write][fused]
-    FastKernel fast_k[2][2];
-    if (fast_minb >= 5) {
-        fast_k[0][0] = k_hull_fast<false, 5, false>, fast_k[0][1] = k_hull_fast<false, 5, true>;
-        fast_k[1][0] = k_hull_fast<true, 5, false>, fast_k[1][1] = k_hull_fast<true, 5, true>;
-    } else {
-        fast_k[0][0] = k_hull_fast<false, 4, false>, fast_k[0][1] = k_hull_fast<false, 4, true>;
-        fast_k[1][0] = k_hull_fast<true, 4, false>, fast_k[1][1] = k_hull_fast<true, 4, true>;
-    }
     const int32_t fast_cap = (int32_t)((std::min<unsigned long long>(std::max<unsigned long long>(h_max, 4), 1024) + 1) & ~1ULL);
     const size_t fast_smem = HullFastLayout::bytes(fast_cap) * kHullWarps;
     int fast_grid = 1;
     Scratch<uint8_t> redo;
     if (fast_enabled && n > 0) {
         GPL_TRY(redo.get(ctx, (size_t)n));
-        for (int w = 0; w < 2; ++w) GPL_CUDA(cudaFuncSetAttribute(fast_k[w][fast_fused], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-        int occ = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_k[1][fast_fused], kHullWarps * 32, fast_smem) != cudaSuccess || occ < 1) occ = 1;
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        GPL_CUDA(cudaFuncSetAttribute(k_hull_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        int occ = 1;  // 5 CTAs per SM at 258 coordinates: 96 registers (a few spills; 128 registers / 4 CTAs measured the same)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hull_fast<true>, kHullWarps * 32, fast_smem) != cudaSuccess || occ < 1) occ = 1;
         (void)cudaGetLastError();
         fast_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kHullWarps), (int64_t)kSMs * occ));
     }
@@ -788,8 +743,12 @@ extern "C" int gpl_convex_hull(gpl_ctx *ctx, const gpl_array *in, gpl_array **ou
         if (n == 0) return GPL_OK;
         const uint8_t *only = nullptr;
         if (fast_enabled) {
-            fast_k[write ? 1 : 0][fast_fused]<<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off,
-                                                                                                   in->validity, fast_cap, cnt, off, dst, redo.p);
+            if (write)
+                k_hull_fast<true><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
+                                                                                   fast_cap, cnt, off, dst, redo.p);
+            else
+                k_hull_fast<false><<<fast_grid, kHullWarps * 32, fast_smem, ctx->stream>>>(in->type, n, xy, in->geom_off, in->part_off, in->ring_off, in->validity,
+                                                                                    fast_cap, cnt, off, dst, redo.p);
             ctx->launches++;
             only = redo.p;
         }
