@@ -13,10 +13,12 @@
 // stream.  Round 1 walked an edge list for EVERY point (two dependent L2 gathers + ~10 edge rules per point,
 // 20 of 32 lanes active, 0.15 of the HBM roofline).  Round 2 answers most points from a 2-bit raster:
 //
-//   fine cell (arithmetic)  -> 2-bit code from an L2-resident raster (16 cells per 32-bit word):
+//   fine cell (arithmetic)  -> 2-bit code from an L2-resident raster (64-bit words: the codes of 16 cells + the
+//                              polygon row of the coarse cell's candidate #0):
 //                                0 = outside every polygon                       -> id -1, done
 //                                1 / 2 = strictly inside the coarse cell's candidate #0 / #1 and
-//                                        outside every other polygon              -> id from an 8-byte record, done
+//                                        outside every other polygon              -> id from the word (1) or an
+//                                                                                    8-byte record (2), done
 //                                3 = a ring passes through (or near) the cell, or anything else -> WALK
 //   WALK (~13 % of the points on config 2): the point is appended to a per-warp shared-memory queue and the
 //   queue is drained 32 points at a time, so that the edge walk runs with full warps:
@@ -1544,10 +1546,11 @@ __global__ void __launch_bounds__(kQueryThreads, LEAN ? GPL_PIP_LEAN_MINB : GPL_
 
 // ---- the streaming kernel (MODE 0 of round 2) --------------------------------------------------------------
 // Persistent warps; a warp takes tiles of 128 consecutive points (2 KB, two 256-bit loads per lane, the next tile
-// prefetched into registers).  Per point: closed bbox test, fine cell by arithmetic, ONE 32-bit load of the raster
+// prefetched into registers).  Per point: closed bbox test, fine cell by arithmetic, ONE 64-bit load of the raster
 // word (four independent loads in flight per lane), then
 //   code 0      -> -1
-//   code 1 / 2  -> the row of the coarse cell's candidate #0 / #1 (one 8-byte load, 80 KB table: L1 hits)
+//   code 1      -> the row of the coarse cell's candidate #0: the word's upper half
+//   code 2      -> the row of candidate #1 (one 8-byte load from the 80 KB cand01 table)
 //   code 3      -> appended to the warp's shared-memory queue (ballot + popc compaction).
 // Whenever the queue holds 32 points the warp walks them (walk_point) with all lanes active and overwrites their ids;
 // the rest is drained at the end.  ids are written as 64-bit stores (two consecutive points per lane).
@@ -2129,7 +2132,7 @@ extern "C" int gpl_pip_index_build(gpl_ctx *ctx, const gpl_array *polys, gpl_pip
         return v >= 25 && v <= 6400 ? v : 600;
     }();
     // coarse grid: about one cell per part.  Fine grid: 2^rs x 2^rs cells per coarse cell, as fine as a budget of
-    // raster cells allows (2 bits each: 64 M cells = 16 MB, L2-resident next to the FP32 table), at most 2^7, and at
+    // raster cells allows (8 bytes per 16 cells: 64 M cells = 32 MB, L2-resident next to the FP32 table), at most 2^7, and at
     // most 2^20 fine cells per axis (the error analysis of the raster assumes it).
     int64_t G = (int64_t)ceil(sqrt((double)Pa));
     if (G < 1) G = 1;
