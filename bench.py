@@ -682,7 +682,8 @@ def best_cpu_threads(wl, probe):
     cpus = len(all_cpus())
     best, best_rate = cpus, 0.0
     for th in sorted({cpus, max(1, cpus // 2)}, reverse=True):
-        rate, _, _ = wl.cpu_sample(probe, th)
+        # best of two probes: under torchrun the sibling ranks are still starting up (and exiting) during the first one
+        rate = max(wl.cpu_sample(probe, th)[0] for _ in range(2))
         if rate > best_rate:
             best, best_rate = th, rate
     return best
@@ -703,7 +704,7 @@ def run_reference(args, out):
     env.world, env.rank = max(1, args.gpus), 0
     wl = WORKLOADS[args.workload](args.workload, args, env)
     n_sample = args.ref_sample or 2 * wl.default_cpu_sample()
-    threads = best_cpu_threads(wl, max(1, n_sample // 16))
+    threads = best_cpu_threads(wl, max(1, n_sample // 8))
     for _ in range(min(args.warmup, 2)):
         wl.cpu_sample(max(1, n_sample // 8), threads)
     times, desc = [], ""
