@@ -20,6 +20,11 @@ Other BASELINE configurations are separate arms (`--workload`), same JSON contra
 After the timed region every rank checks its results against the CPU oracle on a bounded slice (`verify` in the JSON
 line) — a number whose results differ from the reference's is not printed at all.
 
+Timing: W (>= 3) warm-up steps, extended with further untimed steps until the device has been under this load for
+MIN_LOAD_S (`config.warmup_steps_run`; nvidia-smi needs that long to deliver `clocks` samples under load — the default timed
+region lasts ~6 ms), then EXACTLY K steps between two CUDA events on the context's stream, barrier + synchronize on both
+sides, max over ranks.
+
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
   python bench.py --impl reference      # the CPU restatement of the reference path on the host cores
@@ -46,6 +51,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "geometries/s"
+MIN_LOAD_S = 0.6  # seconds of warm-up load before the timed region (so that the nvidia-smi clock sampler has samples under load)
 COORD_BYTES = 16  # one f64 xy pair: the algorithmic bytes per coordinate
 
 
@@ -111,7 +117,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)  # one more report after the timed region ended
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -223,8 +229,11 @@ class JoinWorkload:
             xy, _, _ = synth.star_polygons(m, self.grid, self.cell, nv)  # host: libm cos/sin, see synth.py
             self.poly_xy.copy_(torch.from_numpy(xy))
         self.ids = torch.empty(n, dtype=torch.int32, device=e.dev)
-        # one zeroed counts column per step (warm-up included): no fill kernel inside the timed region
+        # one zeroed counts column per timed step: no fill kernel inside the timed region.  Warm-up steps cycle through the
+        # first n_warm columns (the warm-up may be extended for the clock sampler, see _main); their counts are never read.
         self.counts_pool = torch.zeros((e.total_steps, m), dtype=torch.int64, device=e.dev)
+        self.n_warm = max(1, e.total_steps - self.args.steps)
+        self.timed_no = 0
         self.gathered = None
         if self.gather and e.world > 1 and e.rank == 0:
             self.gathered = [torch.empty(n, dtype=torch.int32, device=e.dev) for _ in range(e.world)]
@@ -254,7 +263,11 @@ class JoinWorkload:
         if self.idx is not None:
             self.idx.free()
         self.idx = self.make_index()
-        counts = self.counts_pool[self.step_no]
+        if events is None:
+            counts = self.counts_pool[self.step_no % self.n_warm]
+        else:
+            counts = self.counts_pool[self.n_warm + self.timed_no]
+            self.timed_no += 1
         self.step_no += 1
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -791,9 +804,26 @@ def _main(out):
         sampler = ClockSampler(local)
         if env.rank == 0:
             sampler.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample period
+        t_load = time.perf_counter()
         for _ in range(warmup):
             wl.step(None)
         env.stream.synchronize()
+        # nvidia-smi takes a few hundred ms to start and then reports every 20 ms, the default timed region lasts ~6 ms: keep
+        # the device under the SAME load for MIN_LOAD_S before the timed region (more warm-up steps, in batches, the same
+        # number on every rank) so that `clocks` holds samples taken under load right up to the timed steps.
+        extra_warmup = 0
+        while extra_warmup < 20000:
+            go_on = 1 if time.perf_counter() - t_load < MIN_LOAD_S else 0
+            if env.world > 1:
+                flag = torch.tensor([go_on], dtype=torch.int32, device=env.dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                go_on = int(flag.item())
+            if not go_on:
+                break
+            for _ in range(8):
+                wl.step(None)
+            extra_warmup += 8
+            env.stream.synchronize()
         if env.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -877,6 +907,7 @@ def _main(out):
             "parallelism": f"row-range partition over {env.world} GPU(s)" + (", polygon side replicated" if args.workload in ("c2", "c4") else ""),
             "kernel_ms": dom_ms,
             "op_call_ms": k_mean,
+            "warmup_steps_run": warmup + extra_warmup,
             "timing": ("kernel_ms: CUDA events the library records around each k_pip_stream launch on its stream (gpl_ctx_kernel_timing); "
                        "op_call_ms: events around the whole gpl_contains_join call (counter memset + k_pip_stream + k_pip_deferred)"
                        if kt_n else "kernel_ms = op_call_ms: CUDA events around the op calls on the context's stream"),
