@@ -372,3 +372,77 @@ def test_multi_distance_is_the_minimum_over_members(og, conv):
     empty = GeoArrowArray.from_shapes(GeometryType.MULTIPOINT, [[], [(1.0, 1.0), (4.0, 5.0)]])
     q = GeoArrowArray.points(np.array([[0.0, 0.0], [1.0, 1.0]]))
     assert og.distance_rowwise(conv(empty), conv(q)).tolist() == [1.7976931348623157e308, 0.0]
+
+
+def test_area_centroid_length_envelope_against_exact_rational(og, conv):
+    """random polygons with holes and MultiPolygons at three magnitudes: the shoelace area, the area-weighted centroid, the ring
+    length and the envelope evaluated in exact rational arithmetic on the SAME doubles, against the oracle's f64 loops
+    (geo's `Area`, `Centroid`, `EuclideanLength`, `BoundingRect` restated) — an independent formulation, 1e-12 relative"""
+    from fractions import Fraction as F
+
+    rng = np.random.default_rng(21)
+
+    def ring(cx, cy, r0, r1, n, sc):
+        th = np.sort(rng.uniform(0, 2 * np.pi, n))
+        rr = rng.uniform(r0, r1, n)
+        pts = [(float(sc * (cx + rr[i] * np.cos(th[i]))), float(sc * (cy + rr[i] * np.sin(th[i])))) for i in range(n)]
+        return pts + [pts[0]]
+
+    def shoelace(r):  # signed area (exact) and first moments of a closed ring
+        a = mx = my = F(0)
+        for (x0, y0), (x1, y1) in zip(r[:-1], r[1:]):
+            x0, y0, x1, y1 = F(x0), F(y0), F(x1), F(y1)
+            c = x0 * y1 - x1 * y0
+            a += c
+            mx += (x0 + x1) * c
+            my += (y0 + y1) * c
+        return a / 2, mx / 6, my / 6
+
+    polys, multis = [], []
+    for k in range(60):
+        sc, off = [(1.0, 0.0), (1e-3, 5.0), (250.0, 4000.0)][k % 3]
+        ext = ring(off, -off, 4.0, 9.0, int(rng.integers(5, 40)), sc)
+        holes = [ring(off + dx, -off + dy, 0.3, 0.9, int(rng.integers(3, 9)), sc) for dx, dy in [(-1.5, 0.0), (1.5, 0.5)][: k % 3]]
+        polys.append([ext] + holes)
+    for k in range(20):
+        multis.append([[ring(10.0 * j, 3.0 * k, 1.0, 2.5, int(rng.integers(4, 20)), 1.0)] + ([ring(10.0 * j, 3.0 * k, 0.2, 0.6, 5, 1.0)] if j % 2 else []) for j in range(1 + k % 3)])
+
+    def exact_poly(rings):
+        A = MX = MY = F(0)
+        for i, r in enumerate(rings):
+            a, mx, my = shoelace(r)
+            s = 1 if a >= 0 else -1  # orientation-independent: |exterior| - sum |holes|
+            w = 1 if i == 0 else -1
+            A += w * s * a
+            MX += w * s * mx
+            MY += w * s * my
+        return A, MX, MY
+
+    for typ, shapes in ((GeometryType.POLYGON, polys), (GeometryType.MULTIPOLYGON, multis)):
+        arr = GeoArrowArray.from_shapes(typ, shapes)
+        area = og.area(conv(arr))
+        cen, valid = og.centroid(conv(arr))
+        length = og.euclidean_length(conv(arr))
+        env, ev = og.envelope(conv(arr))
+        assert valid.all() and ev.all()
+        for i, shp in enumerate(shapes):
+            parts = [shp] if typ == GeometryType.POLYGON else shp
+            A = MX = MY = F(0)
+            for rings in parts:
+                a, mx, my = exact_poly(rings)
+                A, MX, MY = A + a, MX + mx, MY + my
+            assert abs(area[i] - float(A)) <= 1e-12 * abs(float(A))
+            cx, cy = float(MX / A), float(MY / A)
+            scale = max(abs(cx), abs(cy), 1e-300)
+            assert abs(cen[i, 0] - cx) <= 1e-9 * scale and abs(cen[i, 1] - cy) <= 1e-9 * scale
+            coords = [c for rings in parts for r in rings for c in r]
+            xs, ys = [c[0] for c in coords], [c[1] for c in coords]
+            ext_coords = [c for rings in parts for c in rings[0]]
+            assert env[i].tolist() == [min(c[0] for c in ext_coords), min(c[1] for c in ext_coords), max(c[0] for c in ext_coords), max(c[1] for c in ext_coords)] \
+                or env[i].tolist() == [min(xs), min(ys), max(xs), max(ys)]
+            # euclidean_length of an areal row = the length of its exterior ring(s) (the reference maps polygons to their exterior,
+            # geoseries.rs:35-41); correctly rounded sum of hypots as the yardstick
+            import math
+
+            want_len = math.fsum(math.hypot(b[0] - a[0], b[1] - a[1]) for rings in parts for a, b in zip(rings[0][:-1], rings[0][1:]))
+            assert abs(length[i] - want_len) <= 1e-12 * want_len
