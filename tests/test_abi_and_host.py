@@ -107,3 +107,31 @@ def test_bundled_datasets_are_arrow_ipc_files():
         assert t.num_rows == rows[name] and t.schema.field("geometry").type == "binary"
     with pytest.raises(ValueError):
         datasets.get_path("nope")
+
+
+def test_accessor_mirrors_the_reference_surface():
+    """every entry point of the reference's `.geo` accessor (py-geopolars/python/geopolars/internals/georust/geoseries.py:22-309)
+    and every method of its Rust trait (geopolars/geopolars-geo/src/geoseries.rs:10-181) exists under the same name, as a
+    property where the reference has a property, with the reference's parameter names and defaults"""
+    import inspect
+
+    from geopolars_b200.geoseries import GeoRustSeries
+
+    properties = ["area", "centroid", "geom_type", "x", "y"]
+    methods = {
+        "affine_transform": ["matrix"], "convex_hull": [], "envelope": [], "euclidean_length": [], "exterior": [],
+        "geodesic_length": ["method"], "is_empty": [], "is_ring": [], "rotate": ["angle", "origin"], "scale": ["xfact", "yfact", "origin"],
+        "skew": ["xs", "ys", "origin"], "distance": ["other"], "translate": ["xoff", "yoff"],
+        # trait methods the Python accessor of the reference does not expose yet (geoseries.rs:47-53, 126-139)
+        "explode": [], "simplify": ["tolerance"],
+    }
+    for p in properties:
+        assert isinstance(inspect.getattr_static(GeoRustSeries, p), property), p
+    for name, params in methods.items():
+        fn = inspect.getattr_static(GeoRustSeries, name)
+        assert callable(fn) and not isinstance(fn, property), name
+        assert list(inspect.signature(fn).parameters)[1:] == params, (name, list(inspect.signature(fn).parameters))
+    sig = inspect.signature(GeoRustSeries.rotate)
+    assert sig.parameters["origin"].default == "center"  # georust/geoseries.py:187
+    assert inspect.signature(GeoRustSeries.geodesic_length).parameters["method"].default == "geodesic"  # :128
+    assert inspect.signature(GeoRustSeries.translate).parameters["xoff"].default == 0.0  # :278
